@@ -1,0 +1,186 @@
+/*
+ * b2sense.h -- C ABI of the B200 sensor-readout engine (libb2sense.so).
+ *
+ * This is the drop-in boundary under the two wrapper classes of the reference plugin
+ * (ref = yassine-cherni/mujoco_ros2_simulation):
+ *   MujocoLidar    ref:include/mujoco_ros2_control/mujoco_lidar.hpp:74-92,  ref:src/mujoco_lidar.cpp
+ *   MujocoCameras  ref:include/mujoco_ros2_control/mujoco_cameras.hpp:82-101, ref:src/mujoco_cameras.cpp
+ * and under the rangefinder work MuJoCo does inside mj_step
+ * (ref:src/mujoco_system_interface.cpp:1691,1731 -> engine_sensor.c / engine_ray.c, MuJoCo 3.3.4).
+ *
+ * Conventions
+ *   - plain C, no C++ types, no exceptions cross the boundary;
+ *   - every call returns B2_OK (0) or a negative b2_status; b2_last_error() gives the text
+ *     (thread-local);
+ *   - handles are opaque; every output buffer is caller-allocated;
+ *   - "_device" entry points take device pointers, enqueue on the scene's stream and return
+ *     without blocking; the plain entry points take HOST pointers, stage through pinned memory
+ *     and block until the result is in the caller's buffer;
+ *   - there is NO CPU fallback: every entry point fails with B2_ERR_CUDA when no sm_100 device
+ *     is usable.
+ *   - mjModel / mjData field names are kept so a binding is `desc.geom_type = m->geom_type;`.
+ */
+#ifndef B2SENSE_H
+#define B2SENSE_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B2_VERSION 100 /* 0.1.0 */
+#define B2_NGROUP 6    /* mjNGROUP */
+
+typedef enum b2_status {
+  B2_OK = 0,
+  B2_ERR_INVALID = -1,     /* bad argument (null handle, negative count, bad enum ...) */
+  B2_ERR_CUDA = -2,        /* CUDA runtime error or no usable device */
+  B2_ERR_UNSUPPORTED = -3, /* geom type the engine does not implement (hfield, sdf) */
+  B2_ERR_NOMEM = -4
+} b2_status;
+
+/* mjtGeom values the engine accepts (mujoco/mjmodel.h) */
+enum {
+  B2_GEOM_PLANE = 0,
+  B2_GEOM_SPHERE = 2,
+  B2_GEOM_CAPSULE = 3,
+  B2_GEOM_ELLIPSOID = 4,
+  B2_GEOM_CYLINDER = 5,
+  B2_GEOM_BOX = 6,
+  B2_GEOM_MESH = 7
+};
+
+typedef struct b2_scene b2_scene;
+typedef struct b2_lidar b2_lidar;
+typedef struct b2_camera b2_camera;
+
+/* Static model: the mjModel fields read by ray_eliminate / mju_rayGeom / mj_rayMesh
+ * (SURVEY.md A.1).  Arrays are copied by b2_scene_create; the caller keeps ownership. */
+typedef struct b2_model_desc {
+  int32_t ngeom, nbody, nmesh, nmat;
+  const int32_t* geom_type;    /* [ngeom] mjtGeom */
+  const int32_t* geom_bodyid;  /* [ngeom] */
+  const int32_t* geom_group;   /* [ngeom] */
+  const int32_t* geom_matid;   /* [ngeom] -1: no material */
+  const int32_t* geom_dataid;  /* [ngeom] mesh id for mesh geoms */
+  const double* geom_size;     /* [ngeom*3] */
+  const float* geom_rgba;      /* [ngeom*4] */
+  const float* mat_rgba;       /* [nmat*4]  (may be NULL when nmat == 0) */
+  const int32_t* body_weldid;  /* [nbody] */
+  const int32_t* mesh_vertadr; /* [nmesh] */
+  const int32_t* mesh_vertnum; /* [nmesh] */
+  const int32_t* mesh_faceadr; /* [nmesh] */
+  const int32_t* mesh_facenum; /* [nmesh] */
+  const float* mesh_vert;      /* [sum(vertnum)*3] */
+  const int32_t* mesh_face;    /* [sum(facenum)*3] vertex ids local to the mesh */
+} b2_model_desc;
+
+/* One lidar = a static table of ray directions in the sensor frame plus the mj_ray arguments the
+ * rangefinder uses (engine_sensor.c) and the LaserScan limits (ref:src/mujoco_lidar.cpp:95-97). */
+typedef struct b2_lidar_desc {
+  int32_t nray;
+  const double* local_dir;  /* [nray*3] ray i in the sensor frame (need not be unit length) */
+  int32_t tile_w;           /* rays per scan line for 2-D tiling of 3-D lidars (0: 1-D) */
+  const uint8_t* geomgroup; /* NULL or [B2_NGROUP] (mj_ray geomgroup) */
+  uint8_t flg_static;       /* mj_ray flg_static (rangefinder: 1) */
+  int32_t bodyexclude;      /* mj_ray bodyexclude (rangefinder: site_bodyid), -1: none */
+  double cutoff;            /* sensor_cutoff; <= 0: none */
+  double range_min;         /* LaserScan range_min (default 0.0) */
+  double range_max;         /* LaserScan range_max (default 1000.0) */
+} b2_lidar_desc;
+
+/* One camera model (ref:src/mujoco_cameras.cpp:43-47,119-124,222-224). */
+typedef struct b2_camera_desc {
+  int32_t width, height; /* cam_resolution */
+  double fovy;           /* cam_fovy, degrees */
+  double znear, zfar;    /* vis.map.znear / zfar */
+  double extent;         /* stat.extent */
+  int32_t point_step;    /* PointCloud2 point_step: 12 (x,y,z) or 16 (x,y,z,pad) */
+} b2_camera_desc;
+
+/* ---- library ------------------------------------------------------------------------------ */
+int b2_version(void);
+int b2_device_count(void); /* number of CUDA devices, 0 if none / no driver */
+const char* b2_last_error(void);
+
+/* ---- scene mirror --------------------------------------------------------------------------
+ * b2_scene_create: called from on_init after LoadModel (ref:src/mujoco_system_interface.cpp:677).
+ * Copies the static model, builds the per-mesh triangle BVHs and allocates nworld pose slots.
+ * The geom BVH topology is built by the first b2_scene_update_poses covering world 0 and refit
+ * on every later update.  stream: a cudaStream_t to enqueue on, or NULL for an internal one. */
+int b2_scene_create(const b2_model_desc* model, int32_t nworld, int32_t device, void* stream,
+                    b2_scene** out);
+int b2_scene_destroy(b2_scene* scene);
+
+/* Per-step pose refresh: mjData geom_xpos [nworld*ngeom*3] / geom_xmat [nworld*ngeom*9] for
+ * worlds [world0, world0+nworld).  Called by the physics thread right after mj_step
+ * (ref:src/mujoco_system_interface.cpp:1691,1731) while it holds sim_mutex_: the host version
+ * copies into pinned staging, enqueues the upload and the BVH refit, and returns. */
+int b2_scene_update_poses(b2_scene* scene, int32_t world0, int32_t nworld,
+                          const double* geom_xpos, const double* geom_xmat);
+int b2_scene_update_poses_device(b2_scene* scene, int32_t world0, int32_t nworld,
+                                 const double* d_geom_xpos, const double* d_geom_xmat);
+/* Rebuild the shared geom-BVH topology from the current poses of `world` (optional; use when
+ * the scene has drifted far from the configuration the topology was built on). */
+int b2_scene_rebuild(b2_scene* scene, int32_t world);
+int b2_scene_sync(b2_scene* scene); /* wait for everything enqueued on the scene's stream */
+
+/* ---- lidar: replaces the rangefinder pass of mj_sensorPos and MujocoLidar::update steps 1-2
+ * (ref:src/mujoco_lidar.cpp:247-271) ------------------------------------------------------- */
+int b2_lidar_create(b2_scene* scene, const b2_lidar_desc* desc, b2_lidar** out);
+int b2_lidar_destroy(b2_lidar* lidar);
+
+/* nscan scans in one launch.  Scan s is cast in world scan_world[s] (NULL: world s % nworld)
+ * from the sensor frame sensor_pos[s*3] / sensor_mat[s*9] (row-major, columns = frame axes).
+ * Outputs, each [nscan*nray], any may be NULL:
+ *   ranges : LaserScan.ranges -- (float)min(cutoff, dist), -1 outside [range_min, range_max]
+ *   geomid : id of the geom hit, -1 for a miss (not affected by the range filter)
+ *   dist   : unfiltered double distance (mj_ray return value after cutoff)
+ *   xyz    : [nscan*nray*3] hit point in the sensor frame, NaN for a filtered / missed ray   */
+int b2_lidar_cast(b2_lidar* lidar, int32_t nscan, const int32_t* scan_world,
+                  const double* sensor_pos, const double* sensor_mat, float* ranges,
+                  int32_t* geomid, double* dist, float* xyz);
+int b2_lidar_cast_device(b2_lidar* lidar, int32_t nscan, const int32_t* d_scan_world,
+                         const double* d_sensor_pos, const double* d_sensor_mat, float* d_ranges,
+                         int32_t* d_geomid, double* d_dist, float* d_xyz);
+
+/* mj_multiRay-shaped entry (MuJoCo 3.3.4 engine_ray.c) on `world`.
+ * Host pointers, blocking.  Hits farther than cutoff are reported as misses. */
+int b2_multiray(b2_scene* scene, int32_t world, const double pnt[3], const double* vec,
+                const uint8_t* geomgroup, uint8_t flg_static, int32_t bodyexclude,
+                int32_t* geomid, double* dist, int32_t nray, double cutoff);
+
+/* ---- depth camera: replaces MujocoCameras::update step 3 (ref:src/mujoco_cameras.cpp:222-240)
+ * and adds the PointCloud2 projection ------------------------------------------------------- */
+int b2_camera_create(b2_scene* scene /* nullable */, int32_t device, const b2_camera_desc* desc,
+                     b2_camera** out);
+int b2_camera_destroy(b2_camera* cam);
+/* CameraInfo K (3x3) and P (3x4) as register_cameras fills them (ref:src/mujoco_cameras.cpp:119-124) */
+int b2_camera_info(const b2_camera* cam, double K[9], double P[12]);
+/* ncam depth buffers of this camera model in one launch.
+ *   gl_depth     [ncam*H*W] float, mjr_readPixels layout (bottom-left origin, 0 near .. 1 far)
+ *   depth32fc1   [ncam*H*W] float, Image 32FC1 data, top-left origin, metres   (nullable)
+ *   cloud        [ncam*H*W*point_step bytes] PointCloud2 data, x,y,z FLOAT32    (nullable)  */
+int b2_depth_to_cloud(b2_camera* cam, int32_t ncam, const float* gl_depth, float* depth32fc1,
+                      void* cloud);
+int b2_depth_to_cloud_device(b2_camera* cam, int32_t ncam, const float* d_gl_depth,
+                             float* d_depth32fc1, void* d_cloud);
+/* N1: depth by ray casting -- fills a GL-layout depth buffer
+ * [ncam*H*W] from the scene mirror for ncam camera poses (MuJoCo camera frame: looks along -Z,
+ * +X right, +Y up), so the GL render + readback (ref:src/mujoco_cameras.cpp:202-219) is not needed. */
+int b2_camera_render_depth_device(b2_camera* cam, int32_t ncam, const int32_t* d_cam_world,
+                                  const double* d_cam_pos, const double* d_cam_mat,
+                                  float* d_gl_depth);
+
+/* ---- introspection used by bench.py / tests ------------------------------------------------ */
+/* number of kernels this library has launched in this process (all scenes / cameras) */
+long long b2_launch_count(void);
+int b2_scene_stats(const b2_scene* scene, int32_t* n_bvh_nodes, int32_t* n_planes,
+                   int64_t* n_mesh_nodes, int64_t* n_mesh_tris);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

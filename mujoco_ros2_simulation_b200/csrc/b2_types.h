@@ -1,0 +1,117 @@
+// b2_types.h -- POD layouts shared by the host runtime and the sm_100a kernels.
+//
+// HBM layout of the scene mirror (DESIGN.md "Data layout"):
+//   GeomStatic  [G]        static per model      32 B  size (f64x3), type, dataid
+//   GeomPose    [W][G]     per world, per step   96 B  xpos (f64x3) + xmat (f64x9), 16-B aligned
+//   BvhNode     [W][N]     geom BVH per world    64 B  both children's fp32 boxes + child links
+//   BvhNode     [sum Nm]   per-mesh triangle BVH 64 B  mesh-local frame, static
+//   MeshTri     [sum T]    triangles in leaf order 48 B  three float4 (xyz + pad)
+#ifndef B2_TYPES_H
+#define B2_TYPES_H
+
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define B2_HD __host__ __device__ __forceinline__
+#define B2_ALIGN(n) __align__(n)
+#else
+#define B2_HD inline
+#define B2_ALIGN(n) alignas(n)
+#endif
+
+namespace b2 {
+
+enum GeomType : int32_t {
+  GEOM_PLANE = 0,
+  GEOM_HFIELD = 1,
+  GEOM_SPHERE = 2,
+  GEOM_CAPSULE = 3,
+  GEOM_ELLIPSOID = 4,
+  GEOM_CYLINDER = 5,
+  GEOM_BOX = 6,
+  GEOM_MESH = 7
+};
+
+constexpr double kMinVal = 1e-15;  // mjMINVAL
+constexpr int kEmptyChild = INT32_MIN;
+
+// A BVH2 node holding the boxes of both children (so one 64-B fetch decides both descents).
+// child >= 0: inner node index; child < 0: leaf, payload = ~child
+//   geom BVH : payload = geom id
+//   mesh BVH : payload = (first_triangle << 2) | (count - 1), triangles relative to the mesh base
+// An absent child has an inverted box (lo = +FLT_MAX, hi = -FLT_MAX) and link kEmptyChild.
+struct B2_ALIGN(16) BvhNode {
+  float lo0[3], hi0[3];
+  float lo1[3], hi1[3];
+  int32_t c0, c1;
+  int32_t pad0, pad1;
+};
+static_assert(sizeof(BvhNode) == 64, "BvhNode must be 64 B");
+
+struct B2_ALIGN(16) GeomStatic {
+  double size[3];
+  int32_t type;
+  int32_t dataid;
+};
+static_assert(sizeof(GeomStatic) == 32, "GeomStatic must be 32 B");
+
+struct B2_ALIGN(16) GeomPose {
+  double pos[3];
+  double mat[9];
+};
+static_assert(sizeof(GeomPose) == 96, "GeomPose must be 96 B");
+
+struct B2_ALIGN(16) MeshTri {
+  float v0[4], v1[4], v2[4];
+};
+static_assert(sizeof(MeshTri) == 48, "MeshTri must be 48 B");
+
+struct MeshInfo {
+  int32_t node_base;  // first BvhNode of this mesh in the mesh-node array
+  int32_t tri_base;   // first MeshTri of this mesh
+  int32_t nnode;
+  int32_t ntri;
+};
+
+// ray generation modes of the cast kernel
+enum CastMode : int32_t {
+  MODE_LIDAR = 0,     // dir = sensor_mat * local_dir[r], LaserScan epilogue
+  MODE_MULTIRAY = 1,  // dir = vec[r] as given (mj_multiRay), (geomid, dist) epilogue
+  MODE_CAMERA = 2     // dir from pinhole intrinsics, GL depth epilogue
+};
+
+// Everything one cast launch reads.  Passed by value as a __grid_constant__ kernel parameter.
+struct CastParams {
+  // scene mirror
+  const BvhNode* tlas;      // [nworld][nnode]
+  const GeomPose* pose;     // [nworld][ngeom]
+  const GeomStatic* gstat;  // [ngeom]
+  const int32_t* plane_ids; // [nplane] geoms kept outside the BVH
+  const MeshInfo* mesh;     // [nmesh]
+  const BvhNode* mnodes;
+  const MeshTri* mtris;
+  int32_t nnode, ngeom, nplane, nworld;
+  // sensor
+  const uint8_t* elim;      // [ngeom] ray_eliminate flags for this sensor
+  const double* local_dir;  // [nray*3] (lidar table or multiray vec)
+  int32_t nray, tile_w, mode;
+  double cutoff, range_min, range_max;
+  // camera mode
+  int32_t cam_w, cam_h;
+  double cam_f, cam_cx, cam_cy;
+  float cam_near, cam_far;
+  // batch
+  int32_t nscan;
+  const int32_t* scan_world;  // nullable
+  const double* spos;         // [nscan*3]
+  const double* smat;         // [nscan*9]
+  // outputs (nullable)
+  float* ranges;
+  int32_t* geomid;
+  double* dist;
+  float* xyz;
+  float* gl_depth;
+};
+
+}  // namespace b2
+#endif

@@ -1,0 +1,234 @@
+// bvh_build.cpp -- binned-SAH BVH2 builder (host, one-off).  See bvh_build.h.
+#include "bvh_build.h"
+
+#include <algorithm>
+#include <cfloat>
+#include <cmath>
+#include <numeric>
+
+namespace b2 {
+namespace {
+
+constexpr int kBins = 16;
+
+struct Tmp {
+  Aabb box;
+  int left = -1, right = -1;  // indices into tmp (inner) or -1
+  int first = 0, count = 0;   // range in `order`
+};
+
+inline void box_reset(Aabb& b) {
+  for (int k = 0; k < 3; k++) {
+    b.lo[k] = FLT_MAX;
+    b.hi[k] = -FLT_MAX;
+  }
+}
+inline void box_grow(Aabb& b, const Aabb& o) {
+  for (int k = 0; k < 3; k++) {
+    b.lo[k] = std::min(b.lo[k], o.lo[k]);
+    b.hi[k] = std::max(b.hi[k], o.hi[k]);
+  }
+}
+inline float box_area(const Aabb& b) {
+  const float dx = b.hi[0] - b.lo[0], dy = b.hi[1] - b.lo[1], dz = b.hi[2] - b.lo[2];
+  if (dx < 0 || dy < 0 || dz < 0) return 0.f;
+  return 2.f * (dx * dy + dy * dz + dz * dx);
+}
+
+struct Builder {
+  const std::vector<Aabb>& prims;
+  std::vector<float> cen;  // [n*3]
+  std::vector<int32_t> order;
+  std::vector<Tmp> tmp;
+  int max_leaf;
+  float cost_isect;
+  int max_depth = 0;
+
+  explicit Builder(const std::vector<Aabb>& p, int ml, float ci)
+      : prims(p), max_leaf(ml), cost_isect(ci) {
+    const int n = (int)p.size();
+    cen.resize((size_t)n * 3);
+    order.resize(n);
+    std::iota(order.begin(), order.end(), 0);
+    for (int i = 0; i < n; i++)
+      for (int k = 0; k < 3; k++) cen[3 * i + k] = 0.5f * (p[i].lo[k] + p[i].hi[k]);
+  }
+
+  int build(int first, int count, int depth) {
+    max_depth = std::max(max_depth, depth);
+    const int id = (int)tmp.size();
+    tmp.emplace_back();
+    Aabb box, cbox;
+    box_reset(box);
+    box_reset(cbox);
+    for (int i = first; i < first + count; i++) {
+      box_grow(box, prims[order[i]]);
+      for (int k = 0; k < 3; k++) {
+        const float c = cen[3 * order[i] + k];
+        cbox.lo[k] = std::min(cbox.lo[k], c);
+        cbox.hi[k] = std::max(cbox.hi[k], c);
+      }
+    }
+    tmp[id].box = box;
+    tmp[id].first = first;
+    tmp[id].count = count;
+    if (count == 1) return id;
+
+    // binned SAH over the three axes
+    float best_cost = FLT_MAX;
+    int best_axis = -1, best_split = -1;
+    for (int axis = 0; axis < 3; axis++) {
+      const float lo = cbox.lo[axis], ext = cbox.hi[axis] - cbox.lo[axis];
+      if (!(ext > 0.f)) continue;
+      Aabb bb[kBins];
+      int bc[kBins] = {0};
+      for (auto& b : bb) box_reset(b);
+      const float scale = kBins / ext;
+      for (int i = first; i < first + count; i++) {
+        int b = (int)((cen[3 * order[i] + axis] - lo) * scale);
+        b = std::min(std::max(b, 0), kBins - 1);
+        bc[b]++;
+        box_grow(bb[b], prims[order[i]]);
+      }
+      float right_area[kBins];
+      int right_cnt[kBins];
+      Aabb acc;
+      box_reset(acc);
+      int cnt = 0;
+      for (int b = kBins - 1; b > 0; b--) {
+        box_grow(acc, bb[b]);
+        cnt += bc[b];
+        right_area[b] = box_area(acc);
+        right_cnt[b] = cnt;
+      }
+      box_reset(acc);
+      cnt = 0;
+      for (int b = 0; b < kBins - 1; b++) {
+        box_grow(acc, bb[b]);
+        cnt += bc[b];
+        if (cnt == 0 || right_cnt[b + 1] == 0) continue;
+        const float cost = box_area(acc) * cnt + right_area[b + 1] * right_cnt[b + 1];
+        if (cost < best_cost) {
+          best_cost = cost;
+          best_axis = axis;
+          best_split = b;
+        }
+      }
+    }
+    const float parent_area = std::max(box_area(box), 1e-30f);
+    if (count <= max_leaf) {
+      const float leaf_cost = cost_isect * count;
+      const float split_cost = 1.0f + cost_isect * best_cost / parent_area;
+      if (best_axis < 0 || leaf_cost <= split_cost) return id;  // stays a leaf
+    }
+    int mid;
+    if (best_axis >= 0) {
+      const float lo = cbox.lo[best_axis], ext = cbox.hi[best_axis] - cbox.lo[best_axis];
+      const float scale = kBins / ext;
+      auto it = std::partition(order.begin() + first, order.begin() + first + count, [&](int p) {
+        int b = (int)((cen[3 * p + best_axis] - lo) * scale);
+        b = std::min(std::max(b, 0), kBins - 1);
+        return b <= best_split;
+      });
+      mid = (int)(it - order.begin());
+    } else {
+      mid = first;  // all centroids coincide
+    }
+    if (mid == first || mid == first + count) {
+      // degenerate: fall back to an index median (keeps coincident duplicates adjacent)
+      mid = first + count / 2;
+      std::sort(order.begin() + first, order.begin() + first + count);
+    }
+    const int l = build(first, mid - first, depth + 1);
+    const int r = build(mid, first + count - mid, depth + 1);
+    tmp[id].left = l;
+    tmp[id].right = r;
+    return id;
+  }
+};
+
+inline void set_child(BvhNode& n, int which, const Aabb* box, int32_t link) {
+  float* lo = which == 0 ? n.lo0 : n.lo1;
+  float* hi = which == 0 ? n.hi0 : n.hi1;
+  for (int k = 0; k < 3; k++) {
+    lo[k] = box ? box->lo[k] : FLT_MAX;
+    hi[k] = box ? box->hi[k] : -FLT_MAX;
+  }
+  (which == 0 ? n.c0 : n.c1) = link;
+}
+
+}  // namespace
+
+BuiltBvh build_bvh(const std::vector<Aabb>& prims, int max_leaf, bool leaf_payload_geom,
+                   float cost_isect) {
+  BuiltBvh out;
+  const int n = (int)prims.size();
+  if (n == 0) return out;
+  if (leaf_payload_geom) max_leaf = 1;
+  max_leaf = std::min(std::max(max_leaf, 1), 4);
+  Builder B(prims, max_leaf, cost_isect);
+  B.tmp.reserve((size_t)2 * n);
+  B.build(0, n, 1);
+  out.order = B.order;
+  out.max_depth = B.max_depth;
+
+  auto leaf_link = [&](const Tmp& t) -> int32_t {
+    if (leaf_payload_geom) return ~(int32_t)B.order[t.first];
+    return ~(int32_t)((t.first << 2) | (t.count - 1));
+  };
+
+  // flatten inner nodes in pre-order so children follow their parent
+  std::vector<int> inner_index(B.tmp.size(), -1);
+  std::vector<int> stack;
+  if (B.tmp[0].left < 0) {
+    // single leaf: synthesise a root whose child 0 is the leaf
+    BvhNode root{};
+    set_child(root, 0, &B.tmp[0].box, leaf_link(B.tmp[0]));
+    set_child(root, 1, nullptr, kEmptyChild);
+    out.nodes.push_back(root);
+  } else {
+    stack.push_back(0);
+    int next = 0;
+    // first pass: assign indices in pre-order
+    std::vector<int> pre;
+    while (!stack.empty()) {
+      const int t = stack.back();
+      stack.pop_back();
+      inner_index[t] = next++;
+      pre.push_back(t);
+      const Tmp& T = B.tmp[t];
+      if (B.tmp[T.right].left >= 0) stack.push_back(T.right);
+      if (B.tmp[T.left].left >= 0) stack.push_back(T.left);
+    }
+    out.nodes.resize(next);
+    for (int t : pre) {
+      const Tmp& T = B.tmp[t];
+      BvhNode node{};
+      const Tmp& L = B.tmp[T.left];
+      const Tmp& R = B.tmp[T.right];
+      set_child(node, 0, &L.box, L.left >= 0 ? inner_index[T.left] : leaf_link(L));
+      set_child(node, 1, &R.box, R.left >= 0 ? inner_index[T.right] : leaf_link(R));
+      out.nodes[inner_index[t]] = node;
+    }
+  }
+
+  // refit schedule: height 0 = both children are leaves
+  const int nn = (int)out.nodes.size();
+  std::vector<int> height(nn, 0);
+  for (int i = nn - 1; i >= 0; i--) {
+    int h = 0;
+    if (out.nodes[i].c0 >= 0) h = std::max(h, height[out.nodes[i].c0] + 1);
+    if (out.nodes[i].c1 >= 0) h = std::max(h, height[out.nodes[i].c1] + 1);
+    height[i] = h;
+  }
+  const int nlevel = nn ? *std::max_element(height.begin(), height.end()) + 1 : 0;
+  out.refit_level_start.assign(nlevel + 1, 0);
+  for (int i = 0; i < nn; i++) out.refit_level_start[height[i] + 1]++;
+  for (int l = 0; l < nlevel; l++) out.refit_level_start[l + 1] += out.refit_level_start[l];
+  out.refit_nodes.resize(nn);
+  std::vector<int> cursor(out.refit_level_start.begin(), out.refit_level_start.end() - 1);
+  for (int i = 0; i < nn; i++) out.refit_nodes[cursor[height[i]]++] = i;
+  return out;
+}
+
+}  // namespace b2

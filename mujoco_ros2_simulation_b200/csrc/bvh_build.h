@@ -1,0 +1,34 @@
+// bvh_build.h -- host-side binned-SAH BVH2 construction (K4, one-off per model / rebuild).
+// Used for the per-mesh triangle BVHs (static, mesh-local frame) and for the topology of the
+// geom BVH (whose boxes are then refit on the device every step).
+#ifndef B2_BVH_BUILD_H
+#define B2_BVH_BUILD_H
+
+#include <vector>
+
+#include "b2_types.h"
+
+namespace b2 {
+
+struct Aabb {
+  float lo[3], hi[3];
+};
+
+struct BuiltBvh {
+  std::vector<BvhNode> nodes;    // children always have a larger index than their parent
+  std::vector<int32_t> order;    // primitive ids in leaf order
+  // refit schedule for the geom BVH: nodes sorted by height (leaves-only nodes first)
+  std::vector<int32_t> refit_nodes;
+  std::vector<int32_t> refit_level_start;  // [nlevel+1] offsets into refit_nodes
+  int max_depth = 0;
+};
+
+// prims: one box per primitive.  max_leaf: primitives per leaf (1 for geoms, <=4 for triangles).
+// leaf_payload_geom: true  -> leaf payload = primitive id (max_leaf must be 1)
+//                    false -> leaf payload = (first << 2) | (count - 1) into `order`
+// cost_isect: SAH cost of one primitive test relative to one node visit.
+BuiltBvh build_bvh(const std::vector<Aabb>& prims, int max_leaf, bool leaf_payload_geom,
+                   float cost_isect);
+
+}  // namespace b2
+#endif

@@ -1,0 +1,402 @@
+// kernels.cu -- hand-written sm_100a kernels of the sensor-readout engine.
+//
+//   K1 refit_kernel           pose packing + bottom-up refit of the per-world geom BVH
+//   K2 cast_kernel            warp-packet BVH traversal, closed-form fp64 leaf tests, fused
+//                             LaserScan / multiRay / GL-depth epilogues
+//   K3 depth_to_cloud_kernel  depth linearise + vertical flip + PointCloud2 projection (streaming)
+//
+// Compile with -fmad=false: distances must be bit-identical to the CPU oracle (see ray_core.cuh).
+// No tensor cores: nothing here is a dense contraction.
+#include <cuda_runtime.h>
+
+#include "kernels.cuh"
+#include "ray_core.cuh"
+
+namespace b2 {
+
+constexpr int kCastThreads = 256;
+constexpr int kCastWarps = kCastThreads / 32;
+constexpr size_t kStageLimit = 96 * 1024;  // largest geom BVH staged in shared memory per CTA
+
+int cast_tiles_per_scan(int nray) { return (nray + 31) / 32; }
+int cast_threads_per_block() { return kCastThreads; }
+size_t cast_stage_limit_bytes() { return kStageLimit; }
+
+// =============================================================================================
+// K1: refit
+// =============================================================================================
+__global__ void __launch_bounds__(128) refit_kernel(const RefitParams p) {
+  const int w_local = blockIdx.x;
+  const int world = p.world0 + w_local;
+  GeomPose* pose = p.pose + (size_t)world * p.ngeom;
+  BvhNode* tlas = p.tlas + (size_t)world * p.nnode;
+
+  // 1. pack mjData geom_xpos / geom_xmat into 16-B aligned GeomPose records
+  if (p.raw_xpos != nullptr) {
+    const double* xp = p.raw_xpos + (size_t)w_local * p.ngeom * 3;
+    const double* xm = p.raw_xmat + (size_t)w_local * p.ngeom * 9;
+    // element-wise copy keeps the global reads and writes coalesced: GeomPose is 12 doubles
+    for (int i = threadIdx.x; i < p.ngeom * 12; i += blockDim.x) {
+      const int g = i / 12, k = i - g * 12;
+      const double v = k < 3 ? xp[g * 3 + k] : xm[g * 9 + (k - 3)];
+      reinterpret_cast<double*>(pose + g)[k] = v;
+    }
+    __syncthreads();
+  }
+
+  // 2. bottom-up: level 0 nodes have only geom leaves, level l nodes only children below l
+  for (int l = 0; l < p.nlevel; l++) {
+    const int beg = p.level_start[l], end = p.level_start[l + 1];
+    for (int i = beg + threadIdx.x; i < end; i += blockDim.x) {
+      const int node = p.refit_nodes[i];
+      BvhNode n = p.topo[node];
+#pragma unroll
+      for (int c = 0; c < 2; c++) {
+        const int32_t link = c ? n.c1 : n.c0;
+        float* lo = c ? n.lo1 : n.lo0;
+        float* hi = c ? n.hi1 : n.hi0;
+        if (link == kEmptyChild) {
+          lo[0] = lo[1] = lo[2] = FLT_MAX;
+          hi[0] = hi[1] = hi[2] = -FLT_MAX;
+        } else if (link < 0) {
+          const int g = ~link;
+          const GeomStatic gs = p.gstat[g];
+          geom_aabb(gs.type, gs.size, pose[g], lo, hi);
+        } else {
+          const BvhNode ch = tlas[link];  // written by this CTA at a lower level
+#pragma unroll
+          for (int k = 0; k < 3; k++) {
+            lo[k] = fminf(ch.lo0[k], ch.lo1[k]);
+            hi[k] = fmaxf(ch.hi0[k], ch.hi1[k]);
+          }
+        }
+      }
+      tlas[node] = n;
+    }
+    __syncthreads();
+  }
+}
+
+cudaError_t launch_refit(const RefitParams& p, cudaStream_t stream) {
+  if (p.nworld <= 0) return cudaSuccess;
+  int threads = 32;
+  while (threads < 128 && threads < p.ngeom * 2) threads *= 2;
+  refit_kernel<<<p.nworld, threads, 0, stream>>>(p);
+  return cudaGetLastError();
+}
+
+// =============================================================================================
+// K2: cast
+// =============================================================================================
+struct DevWarp {
+  int32_t* stack;  // this warp's slice of shared memory
+  int lane;
+  __device__ __forceinline__ unsigned ballot(bool pred) const {
+    return __ballot_sync(0xffffffffu, pred);
+  }
+  __device__ __forceinline__ int popc(unsigned m) const { return __popc(m); }
+  __device__ __forceinline__ void push(int& sp, int32_t v) {
+    if (sp < kPacketStack) {
+      if (lane == 0) stack[sp] = v;
+      sp++;
+    }
+    __syncwarp();
+  }
+  __device__ __forceinline__ int32_t pop(int& sp) {
+    --sp;
+    return stack[sp];
+  }
+};
+
+template <bool STAGE>
+struct DevLd {
+  static __device__ __forceinline__ BvhNode load_ro(const BvhNode* ptr) {
+    BvhNode n;
+    const float4* q = reinterpret_cast<const float4*>(ptr);
+    float4* o = reinterpret_cast<float4*>(&n);
+    o[0] = __ldg(q);
+    o[1] = __ldg(q + 1);
+    o[2] = __ldg(q + 2);
+    o[3] = __ldg(q + 3);
+    return n;
+  }
+  __device__ __forceinline__ BvhNode node(const BvhNode* ptr) const { return load_ro(ptr); }
+  __device__ __forceinline__ BvhNode tlas_node(const BvhNode* ptr) const {
+    if (STAGE) {
+      BvhNode n;
+      const float4* q = reinterpret_cast<const float4*>(ptr);  // shared memory
+      float4* o = reinterpret_cast<float4*>(&n);
+      o[0] = q[0];
+      o[1] = q[1];
+      o[2] = q[2];
+      o[3] = q[3];
+      return n;
+    }
+    return load_ro(ptr);
+  }
+  __device__ __forceinline__ MeshTri tri(const MeshTri* ptr) const {
+    MeshTri t;
+    const float4* q = reinterpret_cast<const float4*>(ptr);
+    float4* o = reinterpret_cast<float4*>(&t);
+    o[0] = __ldg(q);
+    o[1] = __ldg(q + 1);
+    o[2] = __ldg(q + 2);
+    return t;
+  }
+  __device__ __forceinline__ GeomPose pose(const GeomPose* ptr) const {
+    GeomPose P;
+    const double2* q = reinterpret_cast<const double2*>(ptr);
+    double2* o = reinterpret_cast<double2*>(&P);
+#pragma unroll
+    for (int i = 0; i < 6; i++) o[i] = __ldg(q + i);
+    return P;
+  }
+  __device__ __forceinline__ GeomStatic gstat(const GeomStatic* ptr) const {
+    GeomStatic g;
+    const double2* q = reinterpret_cast<const double2*>(ptr);
+    double2* o = reinterpret_cast<double2*>(&g);
+    o[0] = __ldg(q);
+    o[1] = __ldg(q + 1);
+    return g;
+  }
+};
+
+// ray index of (tile, lane): 8x4 tiles over (scan line, line index) for 3-D sensors, else 32x1
+__device__ __forceinline__ int tile_ray(int tile, int lane, int tiles_x, int tile_w) {
+  if (tiles_x > 0) {
+    const int ty = tile / tiles_x, tx = tile - ty * tiles_x;
+    return (ty * 4 + (lane >> 3)) * tile_w + tx * 8 + (lane & 7);
+  }
+  return tile * 32 + lane;
+}
+
+template <int MODE, bool STAGE>
+__global__ void __launch_bounds__(kCastThreads)
+    cast_kernel(const __grid_constant__ CastParams p, const int tiles_per_block,
+                const int tiles_per_scan, const int chunks_per_scan, const int tiles_x) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  int32_t* stacks = reinterpret_cast<int32_t*>(smem_raw);
+  BvhNode* s_tlas = reinterpret_cast<BvhNode*>(smem_raw + kCastWarps * kPacketStack * sizeof(int32_t));
+
+  const int warp_id = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int scan = blockIdx.x / chunks_per_scan;
+  const int chunk = blockIdx.x - scan * chunks_per_scan;
+  const int world = p.scan_world ? p.scan_world[scan] : scan % p.nworld;
+
+  const BvhNode* tlas = p.tlas + (size_t)world * p.nnode;
+  if (STAGE) {
+    const float4* src = reinterpret_cast<const float4*>(tlas);
+    float4* dst = reinterpret_cast<float4*>(s_tlas);
+    for (int i = threadIdx.x; i < p.nnode * 4; i += kCastThreads) dst[i] = __ldg(src + i);
+    __syncthreads();
+    tlas = s_tlas;
+  }
+  const GeomPose* pose = p.pose + (size_t)world * p.ngeom;
+
+  // sensor frame (warp-uniform)
+  double o[3], R[9];
+#pragma unroll
+  for (int k = 0; k < 3; k++) o[k] = __ldg(p.spos + (size_t)scan * 3 + k);
+  if (MODE != MODE_MULTIRAY) {
+#pragma unroll
+    for (int k = 0; k < 9; k++) R[k] = __ldg(p.smat + (size_t)scan * 9 + k);
+  }
+
+  DevWarp warp{stacks + warp_id * kPacketStack, lane};
+  const DevLd<STAGE> ld;
+  const float tcap = (MODE == MODE_MULTIRAY) ? f32_up(p.cutoff) : FLT_MAX;
+
+  for (int t = warp_id; t < tiles_per_block; t += kCastWarps) {
+    const int tile = chunk * tiles_per_block + t;
+    if (tile >= tiles_per_scan) break;  // warp-uniform
+    const int r = tile_ray(tile, lane, tiles_x, p.tile_w);
+    bool active = r < p.nray;
+    const int rr = active ? r : 0;
+
+    double l[3], vec[3];
+    active = cast_make_ray(p, MODE, R, rr, l, vec) && active;
+
+    const Hit hit = trace_ray(p, tlas, pose, active, o, vec, tcap, warp, ld);
+
+    if (r < p.nray) cast_epilogue(p, MODE, scan, r, hit, l);
+  }
+}
+
+template <int MODE>
+static cudaError_t launch_cast_mode(const CastParams& p, bool stage, int tiles_per_block,
+                                    cudaStream_t stream) {
+  // 2-D tiling when the sensor is a grid of scan lines
+  int tiles_x = 0;
+  int tiles_per_scan = cast_tiles_per_scan(p.nray);
+  if (p.tile_w > 0 && p.tile_w % 8 == 0 && p.nray % p.tile_w == 0) {
+    const int rows = p.nray / p.tile_w;
+    if (rows >= 4 && rows % 4 == 0) {
+      tiles_x = p.tile_w / 8;
+      tiles_per_scan = tiles_x * (rows / 4);
+    }
+  }
+  if (tiles_per_block < kCastWarps) tiles_per_block = kCastWarps;
+  const int chunks_per_scan = (tiles_per_scan + tiles_per_block - 1) / tiles_per_block;
+  const long long nblocks = (long long)p.nscan * chunks_per_scan;
+  if (nblocks <= 0) return cudaSuccess;
+  if (nblocks > 0x7fffffffLL) return cudaErrorInvalidConfiguration;
+  size_t smem = kCastWarps * kPacketStack * sizeof(int32_t);
+  if (stage) smem += (size_t)p.nnode * sizeof(BvhNode);
+  cudaError_t err;
+  if (stage) {
+    auto k = cast_kernel<MODE, true>;
+    err = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (err != cudaSuccess) return err;
+    k<<<(unsigned)nblocks, kCastThreads, smem, stream>>>(p, tiles_per_block, tiles_per_scan,
+                                                         chunks_per_scan, tiles_x);
+  } else {
+    auto k = cast_kernel<MODE, false>;
+    k<<<(unsigned)nblocks, kCastThreads, smem, stream>>>(p, tiles_per_block, tiles_per_scan,
+                                                         chunks_per_scan, tiles_x);
+  }
+  return cudaGetLastError();
+}
+
+cudaError_t launch_cast(const CastParams& p, bool stage_tlas, int tiles_per_block,
+                        cudaStream_t stream) {
+  if (p.nnode == 0 || (size_t)p.nnode * sizeof(BvhNode) > kStageLimit) stage_tlas = false;
+  switch (p.mode) {
+    case MODE_LIDAR:
+      return launch_cast_mode<MODE_LIDAR>(p, stage_tlas, tiles_per_block, stream);
+    case MODE_MULTIRAY:
+      return launch_cast_mode<MODE_MULTIRAY>(p, stage_tlas, tiles_per_block, stream);
+    case MODE_CAMERA:
+      return launch_cast_mode<MODE_CAMERA>(p, stage_tlas, tiles_per_block, stream);
+    default:
+      return cudaErrorInvalidValue;
+  }
+}
+
+// =============================================================================================
+// K3: depth linearise + flip + PointCloud2 projection
+//   per pixel: 4 B read, 4 B (32FC1) + point_step B (cloud) written; nothing is re-read.
+//   Each thread owns 4 consecutive pixels of one output row; the xyz triples are transposed
+//   through shared memory so every global store instruction writes 512 contiguous bytes.
+// =============================================================================================
+constexpr int kDepthThreads = 256;
+
+template <int PF>  // floats per point: 3 or 4
+__global__ void __launch_bounds__(kDepthThreads) depth_to_cloud_kernel(const DepthParams p) {
+  __shared__ __align__(16) float s_pts[kDepthThreads / 32][32 * 4 * PF];
+  const int quads_per_row = p.width >> 2;
+  const long long quads_per_cam = (long long)quads_per_row * p.height;
+  const long long total = quads_per_cam * p.ncam;
+  const int lane = threadIdx.x & 31, warp_id = threadIdx.x >> 5;
+  const float qnan = __int_as_float(0x7fc00000);
+  float* sw = s_pts[warp_id];
+
+  // warp-contiguous blocks of 32 quads (128 pixels)
+  const long long warp_base0 = ((long long)blockIdx.x * (kDepthThreads / 32) + warp_id) * 32;
+  const long long warp_stride = (long long)gridDim.x * kDepthThreads;
+  for (long long wb = warp_base0; wb < total; wb += warp_stride) {
+    const long long q = wb + lane;
+    const bool ok = q < total;
+    float z[4] = {0.f, 0.f, 0.f, 0.f};
+    int v = 0, u0 = 0;
+    long long opix = 0;
+    if (ok) {
+      const int cam = (int)(q / quads_per_cam);
+      const long long rem = q - (long long)cam * quads_per_cam;
+      v = (int)(rem / quads_per_row);
+      u0 = (int)(rem - (long long)v * quads_per_row) << 2;
+      const long long cam_pix = (long long)cam * p.width * p.height;
+      // GL rows are bottom-up: output row v reads GL row H-1-v (ref:src/mujoco_cameras.cpp:234)
+      const float4 d = __ldcs(reinterpret_cast<const float4*>(
+          p.gl_depth + cam_pix + (long long)(p.height - 1 - v) * p.width + u0));
+      // ref:src/mujoco_cameras.cpp:235  near / (1.0f - d * depth_scale), float32, unfused
+      z[0] = p.znear / (1.0f - d.x * p.depth_scale);
+      z[1] = p.znear / (1.0f - d.y * p.depth_scale);
+      z[2] = p.znear / (1.0f - d.z * p.depth_scale);
+      z[3] = p.znear / (1.0f - d.w * p.depth_scale);
+      opix = cam_pix + (long long)v * p.width + u0;
+      if (p.depth_out)
+        __stcs(reinterpret_cast<float4*>(p.depth_out + opix), make_float4(z[0], z[1], z[2], z[3]));
+    }
+    if (p.cloud) {
+      // depth_image_proc::convertDepth<float>: x = (u - cx) * z * (1/fx), y likewise, NaN if !finite
+      float pt[4 * PF];
+      const float yv = (float)v - p.cy;
+#pragma unroll
+      for (int i = 0; i < 4; i++) {
+        const bool fin = isfinite(z[i]);
+        const float xu = (float)(u0 + i) - p.cx;
+        pt[i * PF + 0] = fin ? xu * z[i] * p.inv_fx : qnan;
+        pt[i * PF + 1] = fin ? yv * z[i] * p.inv_fy : qnan;
+        pt[i * PF + 2] = fin ? z[i] : qnan;
+        if (PF == 4) pt[i * PF + 3] = 0.0f;
+      }
+      float4* s4 = reinterpret_cast<float4*>(sw);
+#pragma unroll
+      for (int j = 0; j < PF; j++)
+        s4[lane * PF + j] = make_float4(pt[4 * j], pt[4 * j + 1], pt[4 * j + 2], pt[4 * j + 3]);
+      __syncwarp();
+      // the warp's 32 quads are contiguous in the output: 32*4*PF floats from pixel wb*4
+      const long long nvalid = (total - wb) < 32 ? (total - wb) : 32;  // quads
+      float4* g4 = reinterpret_cast<float4*>(p.cloud + (wb * 4) * PF);
+#pragma unroll
+      for (int j = 0; j < PF; j++) {
+        const int e = j * 32 + lane;  // float4 index within the warp's block
+        if (e < nvalid * PF) __stcs(g4 + e, s4[e]);
+      }
+      __syncwarp();
+    }
+  }
+}
+
+// generic fallback for widths that are not a multiple of 4: one pixel per thread
+template <int PF>
+__global__ void __launch_bounds__(kDepthThreads) depth_to_cloud_scalar_kernel(const DepthParams p) {
+  const long long per_cam = (long long)p.width * p.height;
+  const long long total = per_cam * p.ncam;
+  const float qnan = __int_as_float(0x7fc00000);
+  for (long long i = (long long)blockIdx.x * kDepthThreads + threadIdx.x; i < total;
+       i += (long long)gridDim.x * kDepthThreads) {
+    const int cam = (int)(i / per_cam);
+    const long long rem = i - (long long)cam * per_cam;
+    const int v = (int)(rem / p.width), u = (int)(rem - (long long)v * p.width);
+    const float d = p.gl_depth[(long long)cam * per_cam + (long long)(p.height - 1 - v) * p.width + u];
+    const float z = p.znear / (1.0f - d * p.depth_scale);
+    if (p.depth_out) p.depth_out[i] = z;
+    if (p.cloud) {
+      const bool fin = isfinite(z);
+      float* o = p.cloud + i * PF;
+      o[0] = fin ? ((float)u - p.cx) * z * p.inv_fx : qnan;
+      o[1] = fin ? ((float)v - p.cy) * z * p.inv_fy : qnan;
+      o[2] = fin ? z : qnan;
+      if (PF == 4) o[3] = 0.0f;
+    }
+  }
+}
+
+cudaError_t launch_depth_to_cloud(const DepthParams& p, cudaStream_t stream) {
+  const long long npix = (long long)p.ncam * p.width * p.height;
+  if (npix <= 0) return cudaSuccess;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const bool vec4 = (p.width % 4 == 0) && (((uintptr_t)p.gl_depth & 15) == 0) &&
+                    (((uintptr_t)p.depth_out & 15) == 0) && (((uintptr_t)p.cloud & 15) == 0);
+  const long long work = vec4 ? npix / 4 : npix;
+  long long blocks = (work + kDepthThreads - 1) / kDepthThreads;
+  const long long cap = (long long)sms * 16;  // grid-stride beyond 16 CTAs per SM
+  if (blocks > cap) blocks = cap;
+  if (vec4) {
+    if (p.point_floats == 4)
+      depth_to_cloud_kernel<4><<<(unsigned)blocks, kDepthThreads, 0, stream>>>(p);
+    else
+      depth_to_cloud_kernel<3><<<(unsigned)blocks, kDepthThreads, 0, stream>>>(p);
+  } else {
+    if (p.point_floats == 4)
+      depth_to_cloud_scalar_kernel<4><<<(unsigned)blocks, kDepthThreads, 0, stream>>>(p);
+    else
+      depth_to_cloud_scalar_kernel<3><<<(unsigned)blocks, kDepthThreads, 0, stream>>>(p);
+  }
+  return cudaGetLastError();
+}
+
+}  // namespace b2

@@ -1,0 +1,50 @@
+// kernels.cuh -- launch wrappers of the sm_100a kernels (defined in kernels.cu).
+#ifndef B2_KERNELS_CUH
+#define B2_KERNELS_CUH
+
+#include <cuda_runtime.h>
+
+#include "b2_types.h"
+
+namespace b2 {
+
+struct RefitParams {
+  // inputs: either raw mjData arrays for worlds [0, nworld) of this launch ...
+  const double* raw_xpos;  // [nworld][ngeom][3]   (nullable: refit from the packed poses)
+  const double* raw_xmat;  // [nworld][ngeom][9]
+  // ... written to / read from the packed scene mirror of worlds [world0, world0+nworld)
+  GeomPose* pose;           // [nworld_total][ngeom]
+  BvhNode* tlas;            // [nworld_total][nnode]
+  const GeomStatic* gstat;  // [ngeom]
+  const BvhNode* topo;      // [nnode] child links of the shared topology
+  const int32_t* refit_nodes;  // [nnode] nodes sorted by height
+  const int32_t* level_start;  // [nlevel+1]
+  int32_t ngeom, nnode, nlevel, world0, nworld;
+};
+
+struct DepthParams {
+  const float* gl_depth;  // [ncam][H][W] bottom-left origin
+  float* depth_out;       // [ncam][H][W] top-left origin (nullable)
+  float* cloud;           // [ncam][H][W][point_floats] (nullable)
+  int32_t ncam, width, height, point_floats;
+  float znear, zfar, depth_scale;
+  float cx, cy, inv_fx, inv_fy;
+};
+
+// K1: pack poses + refit the geom BVH of nworld worlds.  One CTA per world.
+cudaError_t launch_refit(const RefitParams& p, cudaStream_t stream);
+
+// K2: cast nscan*nray rays.  stage_tlas: copy the world's geom BVH into shared memory per CTA.
+// tiles_per_block: 32-ray tiles one CTA walks through (multiple of the warps per CTA).
+cudaError_t launch_cast(const CastParams& p, bool stage_tlas, int tiles_per_block,
+                        cudaStream_t stream);
+// geometry of the tiling the cast kernel uses for a sensor (for host-side sizing)
+int cast_tiles_per_scan(int nray);
+int cast_threads_per_block();
+size_t cast_stage_limit_bytes();
+
+// K3: depth linearise + flip + PointCloud2 projection.
+cudaError_t launch_depth_to_cloud(const DepthParams& p, cudaStream_t stream);
+
+}  // namespace b2
+#endif

@@ -1,0 +1,916 @@
+// runtime.cu -- host runtime and C ABI of libb2sense.so (include/b2sense.h).
+//
+// Scene mirror: static model copied once, per-world poses packed on the device by K1, geom BVH
+// topology built on the host (binned SAH) from one world's poses and refit per step on the device.
+// There is no CPU compute path: without a usable CUDA device every entry point returns B2_ERR_CUDA.
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/b2sense.h"
+#include "b2_types.h"
+#include "bvh_build.h"
+#include "kernels.cuh"
+#include "ray_core.cuh"
+#include "scene_build.h"
+
+using namespace b2;
+
+namespace {
+
+thread_local std::string g_err;
+std::atomic<long long> g_launches{0};
+
+int fail(int code, const std::string& msg) {
+  g_err = msg;
+  return code;
+}
+
+#define B2_CUDA(call)                                                                      \
+  do {                                                                                     \
+    cudaError_t e_ = (call);                                                               \
+    if (e_ != cudaSuccess)                                                                 \
+      return fail(B2_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));        \
+  } while (0)
+
+template <class T>
+struct DevBuf {
+  T* ptr = nullptr;
+  size_t cap = 0;  // elements
+  cudaError_t reserve(size_t n) {
+    if (n <= cap) return cudaSuccess;
+    if (ptr) cudaFree(ptr);
+    ptr = nullptr;
+    cap = 0;
+    cudaError_t e = cudaMalloc(&ptr, n * sizeof(T));
+    if (e == cudaSuccess) cap = n;
+    return e;
+  }
+  void release() {
+    if (ptr) cudaFree(ptr);
+    ptr = nullptr;
+    cap = 0;
+  }
+};
+
+template <class T>
+struct PinBuf {
+  T* ptr = nullptr;
+  size_t cap = 0;
+  cudaError_t reserve(size_t n) {
+    if (n <= cap) return cudaSuccess;
+    if (ptr) cudaFreeHost(ptr);
+    ptr = nullptr;
+    cap = 0;
+    cudaError_t e = cudaMallocHost(&ptr, n * sizeof(T));
+    if (e == cudaSuccess) cap = n;
+    return e;
+  }
+  void release() {
+    if (ptr) cudaFreeHost(ptr);
+    ptr = nullptr;
+    cap = 0;
+  }
+};
+
+int env_int(const char* name, int dflt) {
+  const char* v = std::getenv(name);
+  return v ? std::atoi(v) : dflt;
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------
+// handles
+// ---------------------------------------------------------------------------------------------
+struct b2_scene {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  cudaStream_t copy_stream = nullptr;
+  bool own_stream = false;
+  int sm_count = 148;
+  int ngeom = 0, nbody = 0, nmesh = 0, nmat = 0, nworld = 0;
+  HostModel hm;  // host copy of the static model
+  // device: static
+  DevBuf<GeomStatic> d_gstat;
+  DevBuf<int32_t> d_plane_ids;
+  DevBuf<MeshInfo> d_mesh;
+  DevBuf<BvhNode> d_mnodes;
+  DevBuf<MeshTri> d_mtris;
+  long long n_mesh_nodes = 0, n_mesh_tris = 0;
+  // device: per world
+  DevBuf<GeomPose> d_pose;
+  DevBuf<BvhNode> d_tlas;
+  // geom BVH topology
+  bool topo_built = false;
+  int nnode = 0, nlevel = 0;
+  DevBuf<BvhNode> d_topo;
+  DevBuf<int32_t> d_refit_nodes, d_level_start;
+  // pose staging (double-buffered pinned host memory + device raw arrays)
+  PinBuf<double> h_stage[2];
+  cudaEvent_t stage_done[2] = {nullptr, nullptr};
+  int stage_flip = 0;
+  DevBuf<double> d_raw;
+  // scratch for b2_multiray
+  DevBuf<double> d_mr_vec, d_mr_dist, d_mr_pnt;
+  DevBuf<int32_t> d_mr_id;
+  DevBuf<uint8_t> d_mr_elim;
+};
+
+struct b2_lidar {
+  b2_scene* scene = nullptr;
+  int nray = 0, tile_w = 0;
+  double cutoff = 0, range_min = 0, range_max = 1000;
+  DevBuf<double> d_local_dir;
+  DevBuf<uint8_t> d_elim;
+  // scratch of the host-pointer entry point
+  DevBuf<double> d_spos, d_smat, d_dist;
+  DevBuf<int32_t> d_world, d_geomid;
+  DevBuf<float> d_ranges, d_xyz;
+  cudaEvent_t chunk_done[2] = {nullptr, nullptr};
+};
+
+struct b2_camera {
+  b2_scene* scene = nullptr;
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  b2_camera_desc desc{};
+  double K[9];
+  float near_f = 0, far_f = 0, depth_scale = 0;
+  DevBuf<float> d_in, d_depth, d_cloud;
+  DevBuf<uint8_t> d_elim;  // no geom eliminated for the ray-cast depth
+  DevBuf<double> d_pos, d_mat;
+};
+
+namespace {
+
+int build_meshes(b2_scene* s, const b2_model_desc* m) {
+  HostMeshes hmesh;
+  std::string err;
+  if (!build_mesh_bvhs(s->nmesh, m->mesh_vertadr, m->mesh_vertnum, m->mesh_faceadr, m->mesh_facenum,
+                       m->mesh_vert, m->mesh_face, env_int("B2_MESH_LEAF", 2), kMeshStack - 2, hmesh,
+                       err))
+    return fail(B2_ERR_INVALID, err);
+  s->n_mesh_nodes = (long long)hmesh.nodes.size();
+  s->n_mesh_tris = (long long)hmesh.tris.size();
+  if (s->nmesh > 0) {
+    B2_CUDA(s->d_mesh.reserve(hmesh.infos.size()));
+    B2_CUDA(cudaMemcpy(s->d_mesh.ptr, hmesh.infos.data(), hmesh.infos.size() * sizeof(MeshInfo),
+                       cudaMemcpyHostToDevice));
+    B2_CUDA(s->d_mnodes.reserve(hmesh.nodes.size() + 1));
+    B2_CUDA(cudaMemcpy(s->d_mnodes.ptr, hmesh.nodes.data(), hmesh.nodes.size() * sizeof(BvhNode),
+                       cudaMemcpyHostToDevice));
+    B2_CUDA(s->d_mtris.reserve(hmesh.tris.size() + 1));
+    if (!hmesh.tris.empty())
+      B2_CUDA(cudaMemcpy(s->d_mtris.ptr, hmesh.tris.data(), hmesh.tris.size() * sizeof(MeshTri),
+                         cudaMemcpyHostToDevice));
+  }
+  return B2_OK;
+}
+
+// topology of the geom BVH from one world's poses (host arrays, [ngeom*3] / [ngeom*9])
+int build_topology(b2_scene* s, const double* xpos, const double* xmat) {
+  BuiltBvh bvh;
+  std::string err;
+  if (!build_geom_topology(s->hm, xpos, xmat, kPacketStack - 2, bvh, err))
+    return fail(B2_ERR_UNSUPPORTED, err);
+  const int nnode = (int)bvh.nodes.size();
+  if (s->topo_built && nnode != s->nnode)
+    return fail(B2_ERR_INVALID, "internal: node count changed on rebuild");
+  s->nnode = nnode;
+  s->nlevel = (int)bvh.refit_level_start.size() - 1;
+  if (s->nlevel < 0) s->nlevel = 0;
+  if (nnode > 0) {
+    B2_CUDA(s->d_topo.reserve((size_t)nnode));
+    B2_CUDA(cudaMemcpyAsync(s->d_topo.ptr, bvh.nodes.data(), (size_t)nnode * sizeof(BvhNode),
+                            cudaMemcpyHostToDevice, s->stream));
+    B2_CUDA(s->d_refit_nodes.reserve((size_t)nnode));
+    B2_CUDA(cudaMemcpyAsync(s->d_refit_nodes.ptr, bvh.refit_nodes.data(),
+                            (size_t)nnode * sizeof(int32_t), cudaMemcpyHostToDevice, s->stream));
+    B2_CUDA(s->d_level_start.reserve((size_t)s->nlevel + 1));
+    B2_CUDA(cudaMemcpyAsync(s->d_level_start.ptr, bvh.refit_level_start.data(),
+                            ((size_t)s->nlevel + 1) * sizeof(int32_t), cudaMemcpyHostToDevice,
+                            s->stream));
+    B2_CUDA(s->d_tlas.reserve((size_t)nnode * s->nworld));
+    // the host vectors die at return: the copies above must have consumed them
+    B2_CUDA(cudaStreamSynchronize(s->stream));
+  }
+  s->topo_built = true;
+  return B2_OK;
+}
+
+int run_refit(b2_scene* s, int world0, int nworld, const double* d_xpos, const double* d_xmat) {
+  RefitParams rp{};
+  rp.raw_xpos = d_xpos;
+  rp.raw_xmat = d_xmat;
+  rp.pose = s->d_pose.ptr;
+  rp.tlas = s->d_tlas.ptr;
+  rp.gstat = s->d_gstat.ptr;
+  rp.topo = s->d_topo.ptr;
+  rp.refit_nodes = s->d_refit_nodes.ptr;
+  rp.level_start = s->d_level_start.ptr;
+  rp.ngeom = s->ngeom;
+  rp.nnode = s->nnode;
+  rp.nlevel = s->nlevel;
+  rp.world0 = world0;
+  rp.nworld = nworld;
+  B2_CUDA(launch_refit(rp, s->stream));
+  g_launches++;
+  return B2_OK;
+}
+
+void fill_cast_scene(const b2_scene* s, CastParams& p) {
+  p.tlas = s->d_tlas.ptr;
+  p.pose = s->d_pose.ptr;
+  p.gstat = s->d_gstat.ptr;
+  p.plane_ids = s->d_plane_ids.ptr;
+  p.mesh = s->d_mesh.ptr;
+  p.mnodes = s->d_mnodes.ptr;
+  p.mtris = s->d_mtris.ptr;
+  p.nnode = s->nnode;
+  p.ngeom = s->ngeom;
+  p.nplane = (int)s->hm.plane_ids.size();
+  p.nworld = s->nworld;
+}
+
+// CTA sizing: enough CTAs to fill the machine several times over, but as many tiles per CTA as
+// that allows so the shared-memory staging of the geom BVH is amortised.
+void cast_shape(const b2_scene* s, const CastParams& p, bool& stage, int& tiles_per_block) {
+  const int warps = cast_threads_per_block() / 32;
+  const long long tiles = (long long)cast_tiles_per_scan(p.nray) * p.nscan;
+  const long long want_blocks = (long long)s->sm_count * 16;
+  long long tpb = tiles / want_blocks;
+  tpb = (tpb / warps) * warps;
+  if (tpb < warps) tpb = warps;
+  if (tpb > 8 * warps) tpb = 8 * warps;
+  tiles_per_block = env_int("B2_TILES_PER_BLOCK", (int)tpb);
+  const size_t bytes = (size_t)p.nnode * sizeof(BvhNode);
+  stage = bytes > 0 && bytes <= cast_stage_limit_bytes() &&
+          (tiles_per_block >= 4 * warps || bytes <= 4096);
+  const int force = env_int("B2_STAGE", -1);
+  if (force == 0) stage = false;
+  if (force == 1 && bytes > 0 && bytes <= cast_stage_limit_bytes()) stage = true;
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------
+// library
+// ---------------------------------------------------------------------------------------------
+extern "C" {
+
+int b2_version(void) { return B2_VERSION; }
+
+int b2_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
+const char* b2_last_error(void) { return g_err.c_str(); }
+
+long long b2_launch_count(void) { return g_launches.load(); }
+
+// ---------------------------------------------------------------------------------------------
+// scene
+// ---------------------------------------------------------------------------------------------
+int b2_scene_create(const b2_model_desc* m, int32_t nworld, int32_t device, void* stream,
+                    b2_scene** out) {
+  if (!m || !out) return fail(B2_ERR_INVALID, "b2_scene_create: null argument");
+  *out = nullptr;
+  if (m->ngeom < 0 || m->nbody < 1 || m->nmesh < 0 || m->nmat < 0 || nworld < 1)
+    return fail(B2_ERR_INVALID, "b2_scene_create: bad counts");
+  if (m->ngeom > 0 && (!m->geom_type || !m->geom_bodyid || !m->geom_group || !m->geom_matid ||
+                       !m->geom_dataid || !m->geom_size || !m->geom_rgba))
+    return fail(B2_ERR_INVALID, "b2_scene_create: null geom array");
+  if (!m->body_weldid) return fail(B2_ERR_INVALID, "b2_scene_create: null body_weldid");
+  if (m->nmat > 0 && !m->mat_rgba) return fail(B2_ERR_INVALID, "b2_scene_create: null mat_rgba");
+  if (m->nmesh > 0 && (!m->mesh_vertadr || !m->mesh_vertnum || !m->mesh_faceadr ||
+                       !m->mesh_facenum || !m->mesh_vert || !m->mesh_face))
+    return fail(B2_ERR_INVALID, "b2_scene_create: null mesh array");
+  for (int g = 0; g < m->ngeom; g++) {
+    const int t = m->geom_type[g];
+    if (t == GEOM_HFIELD || t < 0 || t > GEOM_MESH)
+      return fail(B2_ERR_UNSUPPORTED, "geom type not supported by the ray engine (hfield/sdf)");
+    if (m->geom_bodyid[g] < 0 || m->geom_bodyid[g] >= m->nbody)
+      return fail(B2_ERR_INVALID, "geom_bodyid out of range");
+    if (t == GEOM_MESH && (m->geom_dataid[g] < 0 || m->geom_dataid[g] >= m->nmesh))
+      return fail(B2_ERR_INVALID, "mesh geom with bad geom_dataid");
+    if (m->geom_matid[g] >= m->nmat) return fail(B2_ERR_INVALID, "geom_matid out of range");
+  }
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    cudaGetLastError();
+    return fail(B2_ERR_CUDA, "no CUDA device: this engine has no CPU fallback");
+  }
+  if (device < 0 || device >= ndev) return fail(B2_ERR_INVALID, "device index out of range");
+  B2_CUDA(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  B2_CUDA(cudaGetDeviceProperties(&prop, device));
+  if (prop.major < 10)
+    return fail(B2_ERR_CUDA, "device is not sm_100 class: libb2sense is built for sm_100a only");
+
+  b2_scene* s = new b2_scene();
+  s->device = device;
+  s->sm_count = prop.multiProcessorCount;
+  s->ngeom = m->ngeom;
+  s->nbody = m->nbody;
+  s->nmesh = m->nmesh;
+  s->nmat = m->nmat;
+  s->nworld = nworld;
+  auto cleanup_fail = [&](int code) {
+    b2_scene_destroy(s);
+    return code;
+  };
+  if (stream) {
+    s->stream = (cudaStream_t)stream;
+  } else {
+    if (cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking) != cudaSuccess)
+      return cleanup_fail(fail(B2_ERR_CUDA, "cudaStreamCreate failed"));
+    s->own_stream = true;
+  }
+  if (cudaStreamCreateWithFlags(&s->copy_stream, cudaStreamNonBlocking) != cudaSuccess)
+    return cleanup_fail(fail(B2_ERR_CUDA, "cudaStreamCreate failed"));
+  for (int i = 0; i < 2; i++)
+    if (cudaEventCreateWithFlags(&s->stage_done[i], cudaEventDisableTiming) != cudaSuccess)
+      return cleanup_fail(fail(B2_ERR_CUDA, "cudaEventCreate failed"));
+
+  const size_t G = (size_t)m->ngeom;
+  HostModel& hm = s->hm;
+  hm.ngeom = m->ngeom;
+  hm.nbody = m->nbody;
+  hm.nmesh = m->nmesh;
+  hm.nmat = m->nmat;
+  hm.geom_type.assign(m->geom_type, m->geom_type + G);
+  hm.geom_bodyid.assign(m->geom_bodyid, m->geom_bodyid + G);
+  hm.geom_group.assign(m->geom_group, m->geom_group + G);
+  hm.geom_matid.assign(m->geom_matid, m->geom_matid + G);
+  hm.geom_dataid.assign(m->geom_dataid, m->geom_dataid + G);
+  hm.geom_size.assign(m->geom_size, m->geom_size + 3 * G);
+  hm.geom_rgba.assign(m->geom_rgba, m->geom_rgba + 4 * G);
+  if (m->nmat > 0) hm.mat_rgba.assign(m->mat_rgba, m->mat_rgba + 4 * (size_t)m->nmat);
+  hm.body_weldid.assign(m->body_weldid, m->body_weldid + m->nbody);
+
+  std::vector<GeomStatic> gs(G);
+  for (size_t g = 0; g < G; g++) {
+    for (int k = 0; k < 3; k++) gs[g].size[k] = m->geom_size[3 * g + k];
+    gs[g].type = m->geom_type[g];
+    gs[g].dataid = m->geom_dataid[g];
+    if (m->geom_type[g] == GEOM_PLANE)
+      hm.plane_ids.push_back((int32_t)g);
+    else
+      hm.bvh_geoms.push_back((int32_t)g);
+  }
+  auto up = [&](cudaError_t e) { return e == cudaSuccess; };
+  bool ok = up(s->d_gstat.reserve(G + 1)) && up(s->d_plane_ids.reserve(hm.plane_ids.size() + 1)) &&
+            up(s->d_pose.reserve(G * nworld + 1));
+  if (ok && G > 0)
+    ok = up(cudaMemcpy(s->d_gstat.ptr, gs.data(), G * sizeof(GeomStatic), cudaMemcpyHostToDevice));
+  if (ok && !hm.plane_ids.empty())
+    ok = up(cudaMemcpy(s->d_plane_ids.ptr, hm.plane_ids.data(),
+                       hm.plane_ids.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+  if (!ok) {
+    cudaError_t e = cudaGetLastError();
+    return cleanup_fail(fail(B2_ERR_CUDA, std::string("scene upload: ") + cudaGetErrorString(e)));
+  }
+  int rc = build_meshes(s, m);
+  if (rc != B2_OK) return cleanup_fail(rc);
+  *out = s;
+  return B2_OK;
+}
+
+int b2_scene_destroy(b2_scene* s) {
+  if (!s) return B2_OK;
+  cudaSetDevice(s->device);
+  if (s->stream) cudaStreamSynchronize(s->stream);
+  if (s->copy_stream) {
+    cudaStreamSynchronize(s->copy_stream);
+    cudaStreamDestroy(s->copy_stream);
+  }
+  s->d_gstat.release();
+  s->d_plane_ids.release();
+  s->d_mesh.release();
+  s->d_mnodes.release();
+  s->d_mtris.release();
+  s->d_pose.release();
+  s->d_tlas.release();
+  s->d_topo.release();
+  s->d_refit_nodes.release();
+  s->d_level_start.release();
+  s->d_raw.release();
+  s->d_mr_vec.release();
+  s->d_mr_dist.release();
+  s->d_mr_pnt.release();
+  s->d_mr_id.release();
+  s->d_mr_elim.release();
+  for (int i = 0; i < 2; i++) {
+    s->h_stage[i].release();
+    if (s->stage_done[i]) cudaEventDestroy(s->stage_done[i]);
+  }
+  if (s->own_stream && s->stream) cudaStreamDestroy(s->stream);
+  delete s;
+  return B2_OK;
+}
+
+static int update_poses_common(b2_scene* s, int32_t world0, int32_t nworld, const double* xpos,
+                               const double* xmat, bool on_device) {
+  if (!s) return fail(B2_ERR_INVALID, "null scene");
+  if (!xpos || !xmat) return fail(B2_ERR_INVALID, "null pose array");
+  if (world0 < 0 || nworld < 1 || world0 + nworld > s->nworld)
+    return fail(B2_ERR_INVALID, "world range out of bounds");
+  B2_CUDA(cudaSetDevice(s->device));
+  if (s->ngeom == 0) return B2_OK;
+  const size_t G = (size_t)s->ngeom;
+  const size_t n3 = G * 3 * nworld, n9 = G * 9 * nworld;
+  const double* d_xpos = xpos;
+  const double* d_xmat = xmat;
+  const double* h_first_pos = xpos;
+  const double* h_first_mat = xmat;
+  std::vector<double> first;  // first world's poses on the host for the topology build
+  if (!on_device) {
+    // pinned double buffer: the caller may reuse its arrays as soon as we return
+    const int f = s->stage_flip;
+    s->stage_flip ^= 1;
+    B2_CUDA(s->h_stage[f].reserve(n3 + n9));
+    B2_CUDA(cudaEventSynchronize(s->stage_done[f]));
+    std::memcpy(s->h_stage[f].ptr, xpos, n3 * sizeof(double));
+    std::memcpy(s->h_stage[f].ptr + n3, xmat, n9 * sizeof(double));
+    B2_CUDA(s->d_raw.reserve(2 * (G * 12 * (size_t)s->nworld)));
+    double* d_dst = s->d_raw.ptr + (size_t)f * (G * 12 * (size_t)s->nworld);
+    B2_CUDA(cudaMemcpyAsync(d_dst, s->h_stage[f].ptr, (n3 + n9) * sizeof(double),
+                            cudaMemcpyHostToDevice, s->stream));
+    B2_CUDA(cudaEventRecord(s->stage_done[f], s->stream));
+    d_xpos = d_dst;
+    d_xmat = d_dst + n3;
+  } else if (!s->topo_built) {
+    first.resize(G * 12);
+    B2_CUDA(cudaMemcpyAsync(first.data(), xpos, G * 3 * sizeof(double), cudaMemcpyDeviceToHost,
+                            s->stream));
+    B2_CUDA(cudaMemcpyAsync(first.data() + G * 3, xmat, G * 9 * sizeof(double),
+                            cudaMemcpyDeviceToHost, s->stream));
+    B2_CUDA(cudaStreamSynchronize(s->stream));
+    h_first_pos = first.data();
+    h_first_mat = first.data() + G * 3;
+  }
+  if (!s->topo_built) {
+    int rc = build_topology(s, h_first_pos, h_first_mat);
+    if (rc != B2_OK) return rc;
+  }
+  return run_refit(s, world0, nworld, d_xpos, d_xmat);
+}
+
+int b2_scene_update_poses(b2_scene* s, int32_t world0, int32_t nworld, const double* geom_xpos,
+                          const double* geom_xmat) {
+  return update_poses_common(s, world0, nworld, geom_xpos, geom_xmat, false);
+}
+
+int b2_scene_update_poses_device(b2_scene* s, int32_t world0, int32_t nworld,
+                                 const double* d_geom_xpos, const double* d_geom_xmat) {
+  return update_poses_common(s, world0, nworld, d_geom_xpos, d_geom_xmat, true);
+}
+
+int b2_scene_rebuild(b2_scene* s, int32_t world) {
+  if (!s) return fail(B2_ERR_INVALID, "null scene");
+  if (world < 0 || world >= s->nworld) return fail(B2_ERR_INVALID, "world out of range");
+  if (!s->topo_built) return fail(B2_ERR_INVALID, "b2_scene_rebuild before any pose update");
+  B2_CUDA(cudaSetDevice(s->device));
+  if (s->ngeom == 0) return B2_OK;
+  const size_t G = (size_t)s->ngeom;
+  std::vector<GeomPose> hp(G);
+  B2_CUDA(cudaMemcpyAsync(hp.data(), s->d_pose.ptr + G * world, G * sizeof(GeomPose),
+                          cudaMemcpyDeviceToHost, s->stream));
+  B2_CUDA(cudaStreamSynchronize(s->stream));
+  std::vector<double> xpos(G * 3), xmat(G * 9);
+  for (size_t g = 0; g < G; g++) {
+    for (int k = 0; k < 3; k++) xpos[3 * g + k] = hp[g].pos[k];
+    for (int k = 0; k < 9; k++) xmat[9 * g + k] = hp[g].mat[k];
+  }
+  int rc = build_topology(s, xpos.data(), xmat.data());
+  if (rc != B2_OK) return rc;
+  return run_refit(s, 0, s->nworld, nullptr, nullptr);
+}
+
+int b2_scene_sync(b2_scene* s) {
+  if (!s) return fail(B2_ERR_INVALID, "null scene");
+  B2_CUDA(cudaSetDevice(s->device));
+  B2_CUDA(cudaStreamSynchronize(s->stream));
+  B2_CUDA(cudaStreamSynchronize(s->copy_stream));
+  return B2_OK;
+}
+
+int b2_scene_stats(const b2_scene* s, int32_t* n_bvh_nodes, int32_t* n_planes,
+                   int64_t* n_mesh_nodes, int64_t* n_mesh_tris) {
+  if (!s) return fail(B2_ERR_INVALID, "null scene");
+  if (n_bvh_nodes) *n_bvh_nodes = s->nnode;
+  if (n_planes) *n_planes = (int32_t)s->hm.plane_ids.size();
+  if (n_mesh_nodes) *n_mesh_nodes = s->n_mesh_nodes;
+  if (n_mesh_tris) *n_mesh_tris = s->n_mesh_tris;
+  return B2_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// lidar
+// ---------------------------------------------------------------------------------------------
+int b2_lidar_create(b2_scene* s, const b2_lidar_desc* d, b2_lidar** out) {
+  if (!s || !d || !out) return fail(B2_ERR_INVALID, "b2_lidar_create: null argument");
+  *out = nullptr;
+  if (d->nray < 0 || (d->nray > 0 && !d->local_dir))
+    return fail(B2_ERR_INVALID, "b2_lidar_create: bad ray table");
+  if (d->bodyexclude >= s->nbody) return fail(B2_ERR_INVALID, "bodyexclude out of range");
+  B2_CUDA(cudaSetDevice(s->device));
+  b2_lidar* l = new b2_lidar();
+  l->scene = s;
+  l->nray = d->nray;
+  l->tile_w = d->tile_w;
+  l->cutoff = d->cutoff;
+  l->range_min = d->range_min;
+  l->range_max = d->range_max;
+  std::vector<uint8_t> elim;
+  eliminate_flags(s->hm, d->geomgroup, d->flg_static, d->bodyexclude, elim);
+  cudaError_t e = l->d_local_dir.reserve((size_t)d->nray * 3 + 1);
+  if (e == cudaSuccess) e = l->d_elim.reserve(elim.size() + 1);
+  if (e == cudaSuccess && d->nray > 0)
+    e = cudaMemcpy(l->d_local_dir.ptr, d->local_dir, (size_t)d->nray * 3 * sizeof(double),
+                   cudaMemcpyHostToDevice);
+  if (e == cudaSuccess && !elim.empty())
+    e = cudaMemcpy(l->d_elim.ptr, elim.data(), elim.size(), cudaMemcpyHostToDevice);
+  for (int i = 0; i < 2 && e == cudaSuccess; i++)
+    e = cudaEventCreateWithFlags(&l->chunk_done[i], cudaEventDisableTiming);
+  if (e != cudaSuccess) {
+    b2_lidar_destroy(l);
+    return fail(B2_ERR_CUDA, std::string("b2_lidar_create: ") + cudaGetErrorString(e));
+  }
+  *out = l;
+  return B2_OK;
+}
+
+int b2_lidar_destroy(b2_lidar* l) {
+  if (!l) return B2_OK;
+  cudaSetDevice(l->scene->device);
+  cudaStreamSynchronize(l->scene->stream);
+  cudaStreamSynchronize(l->scene->copy_stream);
+  l->d_local_dir.release();
+  l->d_elim.release();
+  l->d_spos.release();
+  l->d_smat.release();
+  l->d_dist.release();
+  l->d_world.release();
+  l->d_geomid.release();
+  l->d_ranges.release();
+  l->d_xyz.release();
+  for (int i = 0; i < 2; i++)
+    if (l->chunk_done[i]) cudaEventDestroy(l->chunk_done[i]);
+  delete l;
+  return B2_OK;
+}
+
+static int lidar_launch(b2_lidar* l, int32_t nscan, const int32_t* d_world, const double* d_pos,
+                        const double* d_mat, float* d_ranges, int32_t* d_geomid, double* d_dist,
+                        float* d_xyz, cudaStream_t stream) {
+  b2_scene* s = l->scene;
+  if (nscan == 0 || l->nray == 0) return B2_OK;
+  if (s->ngeom > 0 && !s->topo_built)
+    return fail(B2_ERR_INVALID, "cast before the first b2_scene_update_poses");
+  CastParams p{};
+  fill_cast_scene(s, p);
+  p.elim = l->d_elim.ptr;
+  p.local_dir = l->d_local_dir.ptr;
+  p.nray = l->nray;
+  p.tile_w = l->tile_w;
+  p.mode = MODE_LIDAR;
+  p.cutoff = l->cutoff;
+  p.range_min = l->range_min;
+  p.range_max = l->range_max;
+  p.nscan = nscan;
+  p.scan_world = d_world;
+  p.spos = d_pos;
+  p.smat = d_mat;
+  p.ranges = d_ranges;
+  p.geomid = d_geomid;
+  p.dist = d_dist;
+  p.xyz = d_xyz;
+  bool stage;
+  int tpb;
+  cast_shape(s, p, stage, tpb);
+  B2_CUDA(launch_cast(p, stage, tpb, stream));
+  g_launches++;
+  return B2_OK;
+}
+
+int b2_lidar_cast_device(b2_lidar* l, int32_t nscan, const int32_t* d_scan_world,
+                         const double* d_sensor_pos, const double* d_sensor_mat, float* d_ranges,
+                         int32_t* d_geomid, double* d_dist, float* d_xyz) {
+  if (!l) return fail(B2_ERR_INVALID, "null lidar");
+  if (nscan < 0) return fail(B2_ERR_INVALID, "negative nscan");
+  if (nscan > 0 && (!d_sensor_pos || !d_sensor_mat)) return fail(B2_ERR_INVALID, "null sensor pose");
+  B2_CUDA(cudaSetDevice(l->scene->device));
+  return lidar_launch(l, nscan, d_scan_world, d_sensor_pos, d_sensor_mat, d_ranges, d_geomid,
+                      d_dist, d_xyz, l->scene->stream);
+}
+
+int b2_lidar_cast(b2_lidar* l, int32_t nscan, const int32_t* scan_world, const double* sensor_pos,
+                  const double* sensor_mat, float* ranges, int32_t* geomid, double* dist,
+                  float* xyz) {
+  if (!l) return fail(B2_ERR_INVALID, "null lidar");
+  if (nscan < 0) return fail(B2_ERR_INVALID, "negative nscan");
+  if (nscan == 0 || l->nray == 0) return B2_OK;
+  if (!sensor_pos || !sensor_mat) return fail(B2_ERR_INVALID, "null sensor pose");
+  b2_scene* s = l->scene;
+  B2_CUDA(cudaSetDevice(s->device));
+  const size_t n = (size_t)nscan * l->nray;
+  B2_CUDA(l->d_spos.reserve((size_t)nscan * 3));
+  B2_CUDA(l->d_smat.reserve((size_t)nscan * 9));
+  if (scan_world) B2_CUDA(l->d_world.reserve((size_t)nscan));
+  if (ranges) B2_CUDA(l->d_ranges.reserve(n));
+  if (geomid) B2_CUDA(l->d_geomid.reserve(n));
+  if (dist) B2_CUDA(l->d_dist.reserve(n));
+  if (xyz) B2_CUDA(l->d_xyz.reserve(n * 3));
+  B2_CUDA(cudaMemcpyAsync(l->d_spos.ptr, sensor_pos, (size_t)nscan * 3 * sizeof(double),
+                          cudaMemcpyHostToDevice, s->stream));
+  B2_CUDA(cudaMemcpyAsync(l->d_smat.ptr, sensor_mat, (size_t)nscan * 9 * sizeof(double),
+                          cudaMemcpyHostToDevice, s->stream));
+  if (scan_world)
+    B2_CUDA(cudaMemcpyAsync(l->d_world.ptr, scan_world, (size_t)nscan * sizeof(int32_t),
+                            cudaMemcpyHostToDevice, s->stream));
+  // pipeline: cast chunk k on the compute stream while chunk k-1 drains over PCIe on the copy
+  // stream (the result read-back is 8 B/ray and would otherwise serialise behind the kernel)
+  int nchunk = env_int("B2_E2E_CHUNKS", 8);
+  if (nchunk > nscan) nchunk = nscan;
+  if (nchunk < 1) nchunk = 1;
+  for (int c = 0; c < nchunk; c++) {
+    const int s0 = (int)((long long)nscan * c / nchunk), s1 = (int)((long long)nscan * (c + 1) / nchunk);
+    const int ns = s1 - s0;
+    if (ns <= 0) continue;
+    const size_t off = (size_t)s0 * l->nray, cnt = (size_t)ns * l->nray;
+    int rc = lidar_launch(l, ns, scan_world ? l->d_world.ptr + s0 : nullptr, l->d_spos.ptr + 3 * (size_t)s0,
+                          l->d_smat.ptr + 9 * (size_t)s0, ranges ? l->d_ranges.ptr + off : nullptr,
+                          geomid ? l->d_geomid.ptr + off : nullptr, dist ? l->d_dist.ptr + off : nullptr,
+                          xyz ? l->d_xyz.ptr + 3 * off : nullptr, s->stream);
+    if (rc != B2_OK) return rc;
+    cudaEvent_t ev = l->chunk_done[c & 1];
+    B2_CUDA(cudaEventRecord(ev, s->stream));
+    B2_CUDA(cudaStreamWaitEvent(s->copy_stream, ev, 0));
+    if (ranges)
+      B2_CUDA(cudaMemcpyAsync(ranges + off, l->d_ranges.ptr + off, cnt * sizeof(float),
+                              cudaMemcpyDeviceToHost, s->copy_stream));
+    if (geomid)
+      B2_CUDA(cudaMemcpyAsync(geomid + off, l->d_geomid.ptr + off, cnt * sizeof(int32_t),
+                              cudaMemcpyDeviceToHost, s->copy_stream));
+    if (dist)
+      B2_CUDA(cudaMemcpyAsync(dist + off, l->d_dist.ptr + off, cnt * sizeof(double),
+                              cudaMemcpyDeviceToHost, s->copy_stream));
+    if (xyz)
+      B2_CUDA(cudaMemcpyAsync(xyz + 3 * off, l->d_xyz.ptr + 3 * off, cnt * 3 * sizeof(float),
+                              cudaMemcpyDeviceToHost, s->copy_stream));
+  }
+  B2_CUDA(cudaStreamSynchronize(s->stream));
+  B2_CUDA(cudaStreamSynchronize(s->copy_stream));
+  return B2_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// mj_multiRay-shaped entry
+// ---------------------------------------------------------------------------------------------
+int b2_multiray(b2_scene* s, int32_t world, const double pnt[3], const double* vec,
+                const uint8_t* geomgroup, uint8_t flg_static, int32_t bodyexclude, int32_t* geomid,
+                double* dist, int32_t nray, double cutoff) {
+  if (!s) return fail(B2_ERR_INVALID, "null scene");
+  if (nray < 0) return fail(B2_ERR_INVALID, "negative nray");
+  if (nray == 0) return B2_OK;
+  if (!pnt || !vec || !dist) return fail(B2_ERR_INVALID, "b2_multiray: null argument");
+  if (world < 0 || world >= s->nworld) return fail(B2_ERR_INVALID, "world out of range");
+  if (s->ngeom > 0 && !s->topo_built)
+    return fail(B2_ERR_INVALID, "b2_multiray before the first b2_scene_update_poses");
+  B2_CUDA(cudaSetDevice(s->device));
+  std::vector<uint8_t> elim;
+  eliminate_flags(s->hm, geomgroup, flg_static, bodyexclude, elim);
+  B2_CUDA(s->d_mr_elim.reserve(elim.size() + 1));
+  B2_CUDA(s->d_mr_vec.reserve((size_t)nray * 3));
+  B2_CUDA(s->d_mr_dist.reserve((size_t)nray));
+  B2_CUDA(s->d_mr_id.reserve((size_t)nray + 1));
+  B2_CUDA(s->d_mr_pnt.reserve(3));
+  if (!elim.empty())
+    B2_CUDA(cudaMemcpyAsync(s->d_mr_elim.ptr, elim.data(), elim.size(), cudaMemcpyHostToDevice,
+                            s->stream));
+  B2_CUDA(cudaMemcpyAsync(s->d_mr_vec.ptr, vec, (size_t)nray * 3 * sizeof(double),
+                          cudaMemcpyHostToDevice, s->stream));
+  B2_CUDA(cudaMemcpyAsync(s->d_mr_pnt.ptr, pnt, 3 * sizeof(double), cudaMemcpyHostToDevice,
+                          s->stream));
+  int32_t* d_world = s->d_mr_id.ptr + nray;  // one spare slot holds the world index
+  B2_CUDA(cudaMemcpyAsync(d_world, &world, sizeof(int32_t), cudaMemcpyHostToDevice, s->stream));
+  CastParams p{};
+  fill_cast_scene(s, p);
+  p.elim = s->d_mr_elim.ptr;
+  p.local_dir = s->d_mr_vec.ptr;
+  p.nray = nray;
+  p.tile_w = 0;
+  p.mode = MODE_MULTIRAY;
+  p.cutoff = cutoff;
+  p.nscan = 1;
+  p.scan_world = d_world;
+  p.spos = s->d_mr_pnt.ptr;
+  p.smat = nullptr;
+  p.geomid = s->d_mr_id.ptr;
+  p.dist = s->d_mr_dist.ptr;
+  bool stage;
+  int tpb;
+  cast_shape(s, p, stage, tpb);
+  B2_CUDA(launch_cast(p, stage, tpb, s->stream));
+  g_launches++;
+  B2_CUDA(cudaMemcpyAsync(dist, s->d_mr_dist.ptr, (size_t)nray * sizeof(double),
+                          cudaMemcpyDeviceToHost, s->stream));
+  if (geomid)
+    B2_CUDA(cudaMemcpyAsync(geomid, s->d_mr_id.ptr, (size_t)nray * sizeof(int32_t),
+                            cudaMemcpyDeviceToHost, s->stream));
+  B2_CUDA(cudaStreamSynchronize(s->stream));
+  return B2_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// camera
+// ---------------------------------------------------------------------------------------------
+int b2_camera_create(b2_scene* scene, int32_t device, const b2_camera_desc* d, b2_camera** out) {
+  if (!d || !out) return fail(B2_ERR_INVALID, "b2_camera_create: null argument");
+  *out = nullptr;
+  if (d->width < 1 || d->height < 1) return fail(B2_ERR_INVALID, "bad camera resolution");
+  if (d->point_step != 12 && d->point_step != 16)
+    return fail(B2_ERR_INVALID, "point_step must be 12 or 16");
+  if (!(d->fovy > 0 && d->fovy < 180)) return fail(B2_ERR_INVALID, "bad fovy");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    cudaGetLastError();
+    return fail(B2_ERR_CUDA, "no CUDA device: this engine has no CPU fallback");
+  }
+  if (scene) device = scene->device;
+  if (device < 0 || device >= ndev) return fail(B2_ERR_INVALID, "device index out of range");
+  B2_CUDA(cudaSetDevice(device));
+  b2_camera* c = new b2_camera();
+  c->scene = scene;
+  c->device = device;
+  c->desc = *d;
+  if (scene) {
+    c->stream = scene->stream;
+  } else {
+    if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) {
+      delete c;
+      return fail(B2_ERR_CUDA, "cudaStreamCreate failed");
+    }
+    c->own_stream = true;
+  }
+  // ref:src/mujoco_cameras.cpp:119-124
+  for (int i = 0; i < 9; i++) c->K[i] = 0.0;
+  const double focal_scaling = (1.0 / std::tan((d->fovy * M_PI / 180.0) / 2.0)) * d->height / 2.0;
+  c->K[0] = focal_scaling;
+  c->K[2] = (double)d->width / 2.0;
+  c->K[4] = focal_scaling;
+  c->K[5] = (double)d->height / 2.0;
+  c->K[8] = 1.0;
+  // ref:src/mujoco_cameras.cpp:222-224
+  c->near_f = (float)(d->znear * d->extent);
+  c->far_f = (float)(d->zfar * d->extent);
+  c->depth_scale = 1.0f - c->near_f / c->far_f;
+  *out = c;
+  return B2_OK;
+}
+
+int b2_camera_destroy(b2_camera* c) {
+  if (!c) return B2_OK;
+  cudaSetDevice(c->device);
+  if (c->stream) cudaStreamSynchronize(c->stream);
+  c->d_in.release();
+  c->d_depth.release();
+  c->d_cloud.release();
+  c->d_elim.release();
+  c->d_pos.release();
+  c->d_mat.release();
+  if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
+  delete c;
+  return B2_OK;
+}
+
+int b2_camera_info(const b2_camera* c, double K[9], double P[12]) {
+  if (!c) return fail(B2_ERR_INVALID, "null camera");
+  if (K)
+    for (int i = 0; i < 9; i++) K[i] = c->K[i];
+  if (P) {
+    for (int i = 0; i < 12; i++) P[i] = 0.0;
+    P[0] = c->K[0];
+    P[2] = c->K[2];
+    P[5] = c->K[4];
+    P[6] = c->K[5];
+    P[10] = 1.0;
+  }
+  return B2_OK;
+}
+
+int b2_depth_to_cloud_device(b2_camera* c, int32_t ncam, const float* d_gl_depth,
+                             float* d_depth32fc1, void* d_cloud) {
+  if (!c) return fail(B2_ERR_INVALID, "null camera");
+  if (ncam < 0) return fail(B2_ERR_INVALID, "negative ncam");
+  if (ncam == 0) return B2_OK;
+  if (!d_gl_depth) return fail(B2_ERR_INVALID, "null depth buffer");
+  B2_CUDA(cudaSetDevice(c->device));
+  DepthParams p{};
+  p.gl_depth = d_gl_depth;
+  p.depth_out = d_depth32fc1;
+  p.cloud = (float*)d_cloud;
+  p.ncam = ncam;
+  p.width = c->desc.width;
+  p.height = c->desc.height;
+  p.point_floats = c->desc.point_step / 4;
+  p.znear = c->near_f;
+  p.zfar = c->far_f;
+  p.depth_scale = c->depth_scale;
+  p.cx = (float)c->K[2];
+  p.cy = (float)c->K[5];
+  p.inv_fx = 1.0f / (float)c->K[0];
+  p.inv_fy = 1.0f / (float)c->K[4];
+  B2_CUDA(launch_depth_to_cloud(p, c->stream));
+  g_launches++;
+  return B2_OK;
+}
+
+int b2_depth_to_cloud(b2_camera* c, int32_t ncam, const float* gl_depth, float* depth32fc1,
+                      void* cloud) {
+  if (!c) return fail(B2_ERR_INVALID, "null camera");
+  if (ncam < 0) return fail(B2_ERR_INVALID, "negative ncam");
+  if (ncam == 0) return B2_OK;
+  if (!gl_depth) return fail(B2_ERR_INVALID, "null depth buffer");
+  B2_CUDA(cudaSetDevice(c->device));
+  const size_t npix = (size_t)ncam * c->desc.width * c->desc.height;
+  const size_t pf = (size_t)c->desc.point_step / 4;
+  B2_CUDA(c->d_in.reserve(npix));
+  if (depth32fc1) B2_CUDA(c->d_depth.reserve(npix));
+  if (cloud) B2_CUDA(c->d_cloud.reserve(npix * pf));
+  B2_CUDA(cudaMemcpyAsync(c->d_in.ptr, gl_depth, npix * sizeof(float), cudaMemcpyHostToDevice,
+                          c->stream));
+  int rc = b2_depth_to_cloud_device(c, ncam, c->d_in.ptr, depth32fc1 ? c->d_depth.ptr : nullptr,
+                                    cloud ? c->d_cloud.ptr : nullptr);
+  if (rc != B2_OK) return rc;
+  if (depth32fc1)
+    B2_CUDA(cudaMemcpyAsync(depth32fc1, c->d_depth.ptr, npix * sizeof(float),
+                            cudaMemcpyDeviceToHost, c->stream));
+  if (cloud)
+    B2_CUDA(cudaMemcpyAsync(cloud, c->d_cloud.ptr, npix * pf * sizeof(float),
+                            cudaMemcpyDeviceToHost, c->stream));
+  B2_CUDA(cudaStreamSynchronize(c->stream));
+  return B2_OK;
+}
+
+int b2_camera_render_depth_device(b2_camera* c, int32_t ncam, const int32_t* d_cam_world,
+                                  const double* d_cam_pos, const double* d_cam_mat,
+                                  float* d_gl_depth) {
+  if (!c) return fail(B2_ERR_INVALID, "null camera");
+  if (!c->scene) return fail(B2_ERR_INVALID, "camera was created without a scene");
+  if (ncam < 0) return fail(B2_ERR_INVALID, "negative ncam");
+  if (ncam == 0) return B2_OK;
+  if (!d_cam_pos || !d_cam_mat || !d_gl_depth) return fail(B2_ERR_INVALID, "null argument");
+  b2_scene* s = c->scene;
+  if (s->ngeom > 0 && !s->topo_built)
+    return fail(B2_ERR_INVALID, "render before the first b2_scene_update_poses");
+  B2_CUDA(cudaSetDevice(s->device));
+  if (c->d_elim.cap == 0) {
+    // the renderer hides only invisible geoms (alpha 0); no body / group / static exclusion
+    std::vector<uint8_t> elim;
+    eliminate_flags(s->hm, nullptr, 1, -1, elim);
+    B2_CUDA(c->d_elim.reserve(elim.size() + 1));
+    if (!elim.empty())
+      B2_CUDA(cudaMemcpy(c->d_elim.ptr, elim.data(), elim.size(), cudaMemcpyHostToDevice));
+  }
+  CastParams p{};
+  fill_cast_scene(s, p);
+  p.elim = c->d_elim.ptr;
+  p.local_dir = nullptr;
+  p.nray = c->desc.width * c->desc.height;
+  p.tile_w = c->desc.width;
+  p.mode = MODE_CAMERA;
+  p.cam_w = c->desc.width;
+  p.cam_h = c->desc.height;
+  p.cam_f = c->K[0];
+  p.cam_cx = c->K[2];
+  p.cam_cy = c->K[5];
+  p.cam_near = c->near_f;
+  p.cam_far = c->far_f;
+  p.nscan = ncam;
+  p.scan_world = d_cam_world;
+  p.spos = d_cam_pos;
+  p.smat = d_cam_mat;
+  p.gl_depth = d_gl_depth;
+  bool stage;
+  int tpb;
+  cast_shape(s, p, stage, tpb);
+  B2_CUDA(launch_cast(p, stage, tpb, c->stream));
+  g_launches++;
+  return B2_OK;
+}
+
+}  // extern "C"

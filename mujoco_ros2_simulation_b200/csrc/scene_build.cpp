@@ -1,0 +1,132 @@
+// scene_build.cpp -- see scene_build.h.
+#include "scene_build.h"
+
+#include <cfloat>
+#include <cmath>
+
+#include "ray_core.cuh"
+
+namespace b2 {
+
+void eliminate_flags(const HostModel& m, const uint8_t* geomgroup, uint8_t flg_static,
+                     int bodyexclude, std::vector<uint8_t>& out) {
+  out.assign((size_t)m.ngeom, 0);
+  for (int g = 0; g < m.ngeom; g++) {
+    bool e = false;
+    const int body = m.geom_bodyid[g];
+    if (body == bodyexclude) e = true;
+    const int matid = m.geom_matid[g];
+    if (matid < 0 && m.geom_rgba[4 * (size_t)g + 3] == 0) e = true;
+    if (matid >= 0 && matid < m.nmat && m.mat_rgba[4 * (size_t)matid + 3] == 0) e = true;
+    if (!flg_static && m.body_weldid[body] == 0) e = true;
+    if (geomgroup) {
+      int grp = m.geom_group[g];
+      grp = grp < 0 ? 0 : (grp > 5 ? 5 : grp);
+      if (geomgroup[grp] == 0) e = true;
+    }
+    out[g] = e ? 1 : 0;
+  }
+}
+
+bool build_mesh_bvhs(int nmesh, const int32_t* vertadr, const int32_t* vertnum,
+                     const int32_t* faceadr, const int32_t* facenum, const float* vert_all,
+                     const int32_t* face_all, int max_leaf, int max_depth, HostMeshes& out,
+                     std::string& err) {
+  out.infos.assign((size_t)nmesh, MeshInfo{});
+  out.nodes.clear();
+  out.tris.clear();
+  for (int k = 0; k < nmesh; k++) {
+    const int nf = facenum[k], nv = vertnum[k];
+    const float* vert = vert_all + 3 * (size_t)vertadr[k];
+    const int32_t* face = face_all + 3 * (size_t)faceadr[k];
+    std::vector<Aabb> boxes((size_t)nf);
+    for (int f = 0; f < nf; f++) {
+      Aabb b;
+      for (int j = 0; j < 3; j++) {
+        b.lo[j] = INFINITY;
+        b.hi[j] = -INFINITY;
+      }
+      for (int c = 0; c < 3; c++) {
+        const int vi = face[3 * f + c];
+        if (vi < 0 || vi >= nv) {
+          err = "mesh_face index out of range";
+          return false;
+        }
+        for (int j = 0; j < 3; j++) {
+          b.lo[j] = std::fmin(b.lo[j], vert[3 * vi + j]);
+          b.hi[j] = std::fmax(b.hi[j], vert[3 * vi + j]);
+        }
+      }
+      // pad: the double triangle test accepts points within rounding of the triangle's plane
+      for (int j = 0; j < 3; j++) {
+        const float pad = 1e-6f * std::fmax(std::fabs(b.lo[j]), std::fabs(b.hi[j])) + 1e-9f;
+        b.lo[j] = std::nextafter(b.lo[j] - pad, -INFINITY);
+        b.hi[j] = std::nextafter(b.hi[j] + pad, INFINITY);
+      }
+      boxes[f] = b;
+    }
+    MeshInfo mi;
+    mi.node_base = (int32_t)out.nodes.size();
+    mi.tri_base = (int32_t)out.tris.size();
+    mi.ntri = nf;
+    if (nf == 0) {  // empty mesh: a root with two absent children
+      BvhNode root{};
+      for (int j = 0; j < 3; j++) {
+        root.lo0[j] = root.lo1[j] = FLT_MAX;
+        root.hi0[j] = root.hi1[j] = -FLT_MAX;
+      }
+      root.c0 = root.c1 = kEmptyChild;
+      mi.nnode = 1;
+      out.nodes.push_back(root);
+      out.infos[k] = mi;
+      continue;
+    }
+    BuiltBvh bvh = build_bvh(boxes, max_leaf, false, 3.0f);
+    if (bvh.max_depth > max_depth) {
+      err = "mesh BVH deeper than the traversal stack";
+      return false;
+    }
+    mi.nnode = (int32_t)bvh.nodes.size();
+    out.infos[k] = mi;
+    out.nodes.insert(out.nodes.end(), bvh.nodes.begin(), bvh.nodes.end());
+    for (int i = 0; i < nf; i++) {
+      const int f = bvh.order[i];
+      MeshTri t;
+      for (int j = 0; j < 3; j++) {
+        t.v0[j] = vert[3 * face[3 * f + 0] + j];
+        t.v1[j] = vert[3 * face[3 * f + 1] + j];
+        t.v2[j] = vert[3 * face[3 * f + 2] + j];
+      }
+      t.v0[3] = t.v1[3] = t.v2[3] = 0.f;
+      out.tris.push_back(t);
+    }
+  }
+  return true;
+}
+
+bool build_geom_topology(const HostModel& m, const double* xpos, const double* xmat, int max_depth,
+                         BuiltBvh& out, std::string& err) {
+  std::vector<Aabb> boxes;
+  boxes.reserve(m.bvh_geoms.size());
+  for (int g : m.bvh_geoms) {
+    GeomPose P;
+    for (int k = 0; k < 3; k++) P.pos[k] = xpos[3 * (size_t)g + k];
+    for (int k = 0; k < 9; k++) P.mat[k] = xmat[9 * (size_t)g + k];
+    Aabb b;
+    geom_aabb(m.geom_type[g], &m.geom_size[3 * (size_t)g], P, b.lo, b.hi);
+    boxes.push_back(b);
+  }
+  out = build_bvh(boxes, 1, true, 4.0f);
+  if (out.max_depth > max_depth) {
+    err = "geom BVH deeper than the traversal stack";
+    return false;
+  }
+  // leaf payloads index `boxes`; map them to geom ids
+  for (auto& n : out.nodes) {
+    if (n.c0 < 0 && n.c0 != kEmptyChild) n.c0 = ~m.bvh_geoms[(size_t)(~n.c0)];
+    if (n.c1 < 0 && n.c1 != kEmptyChild) n.c1 = ~m.bvh_geoms[(size_t)(~n.c1)];
+  }
+  return true;
+}
+
+}  // namespace b2

@@ -1,0 +1,221 @@
+// emu.cpp -- CPU EMULATION HARNESS of the cast kernel's traversal logic.  TEST INFRASTRUCTURE ONLY.
+//
+// Compiles the product's __host__ __device__ traversal (csrc/ray_core.cuh: trace_ray, mesh_trace,
+// the fp64 leaf tests, the conservative fp32 slabs, geom_aabb) and its host-side scene
+// construction (csrc/scene_build.cpp, csrc/bvh_build.cpp) for the CPU, with a 1-lane "warp", so
+// the logic that runs on the B200 can be compared with the oracle in the CPU-only test tier.
+// It is never linked into libb2sense.so and is not a fallback: the product has no CPU path.
+#include <cmath>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/b2sense.h"
+#include "../../mujoco_ros2_simulation_b200/csrc/b2_types.h"
+#include "../../mujoco_ros2_simulation_b200/csrc/bvh_build.h"
+#include "../../mujoco_ros2_simulation_b200/csrc/ray_core.cuh"
+#include "../../mujoco_ros2_simulation_b200/csrc/scene_build.h"
+
+using namespace b2;
+
+namespace {
+
+struct HostWarp {
+  int32_t stack[kPacketStack];
+  unsigned ballot(bool p) const { return p ? 1u : 0u; }
+  int popc(unsigned m) const { return __builtin_popcount(m); }
+  void push(int& sp, int32_t v) {
+    if (sp < kPacketStack) stack[sp++] = v;
+  }
+  int32_t pop(int& sp) { return stack[--sp]; }
+};
+
+struct HostLd {
+  BvhNode node(const BvhNode* p) const { return *p; }
+  BvhNode tlas_node(const BvhNode* p) const { return *p; }
+  MeshTri tri(const MeshTri* p) const { return *p; }
+  GeomPose pose(const GeomPose* p) const { return *p; }
+  GeomStatic gstat(const GeomStatic* p) const { return *p; }
+};
+
+struct EmuScene {
+  HostModel hm;
+  HostMeshes meshes;
+  std::vector<GeomStatic> gstat;
+  std::vector<GeomPose> pose;
+  BuiltBvh topo;
+  std::vector<BvhNode> tlas;
+};
+
+// the refit kernel's per-world work, serially (kernels.cu refit_kernel)
+void host_refit(EmuScene& S) {
+  S.tlas = S.topo.nodes;
+  const int nlevel = (int)S.topo.refit_level_start.size() - 1;
+  for (int l = 0; l < nlevel; l++) {
+    for (int i = S.topo.refit_level_start[l]; i < S.topo.refit_level_start[l + 1]; i++) {
+      const int node = S.topo.refit_nodes[i];
+      BvhNode n = S.topo.nodes[node];
+      for (int c = 0; c < 2; c++) {
+        const int32_t link = c ? n.c1 : n.c0;
+        float* lo = c ? n.lo1 : n.lo0;
+        float* hi = c ? n.hi1 : n.hi0;
+        if (link == kEmptyChild) {
+          lo[0] = lo[1] = lo[2] = FLT_MAX;
+          hi[0] = hi[1] = hi[2] = -FLT_MAX;
+        } else if (link < 0) {
+          const int g = ~link;
+          geom_aabb(S.gstat[g].type, S.gstat[g].size, S.pose[g], lo, hi);
+        } else {
+          const BvhNode& ch = S.tlas[link];
+          for (int k = 0; k < 3; k++) {
+            lo[k] = fminf(ch.lo0[k], ch.lo1[k]);
+            hi[k] = fmaxf(ch.hi0[k], ch.hi1[k]);
+          }
+        }
+      }
+      S.tlas[node] = n;
+    }
+  }
+}
+
+bool make_scene(const b2_model_desc* m, const double* xpos, const double* xmat,
+                const double* topo_xpos, const double* topo_xmat, int mesh_leaf, EmuScene& S,
+                std::string& err) {
+  const size_t G = (size_t)m->ngeom;
+  HostModel& hm = S.hm;
+  hm.ngeom = m->ngeom;
+  hm.nbody = m->nbody;
+  hm.nmesh = m->nmesh;
+  hm.nmat = m->nmat;
+  hm.geom_type.assign(m->geom_type, m->geom_type + G);
+  hm.geom_bodyid.assign(m->geom_bodyid, m->geom_bodyid + G);
+  hm.geom_group.assign(m->geom_group, m->geom_group + G);
+  hm.geom_matid.assign(m->geom_matid, m->geom_matid + G);
+  hm.geom_dataid.assign(m->geom_dataid, m->geom_dataid + G);
+  hm.geom_size.assign(m->geom_size, m->geom_size + 3 * G);
+  hm.geom_rgba.assign(m->geom_rgba, m->geom_rgba + 4 * G);
+  if (m->nmat > 0) hm.mat_rgba.assign(m->mat_rgba, m->mat_rgba + 4 * (size_t)m->nmat);
+  hm.body_weldid.assign(m->body_weldid, m->body_weldid + m->nbody);
+  S.gstat.resize(G);
+  S.pose.resize(G);
+  for (size_t g = 0; g < G; g++) {
+    for (int k = 0; k < 3; k++) S.gstat[g].size[k] = m->geom_size[3 * g + k];
+    S.gstat[g].type = m->geom_type[g];
+    S.gstat[g].dataid = m->geom_dataid[g];
+    if (m->geom_type[g] == GEOM_PLANE)
+      hm.plane_ids.push_back((int32_t)g);
+    else
+      hm.bvh_geoms.push_back((int32_t)g);
+    for (int k = 0; k < 3; k++) S.pose[g].pos[k] = xpos[3 * g + k];
+    for (int k = 0; k < 9; k++) S.pose[g].mat[k] = xmat[9 * g + k];
+  }
+  if (!build_mesh_bvhs(m->nmesh, m->mesh_vertadr, m->mesh_vertnum, m->mesh_faceadr,
+                       m->mesh_facenum, m->mesh_vert, m->mesh_face, mesh_leaf, kMeshStack - 2,
+                       S.meshes, err))
+    return false;
+  // topology from (possibly different) poses, boxes refit to the actual poses: exactly what the
+  // runtime does for worlds other than the one the topology was built on
+  if (!build_geom_topology(hm, topo_xpos ? topo_xpos : xpos, topo_xmat ? topo_xmat : xmat,
+                           kPacketStack - 2, S.topo, err))
+    return false;
+  host_refit(S);
+  return true;
+}
+
+void fill_params(const EmuScene& S, CastParams& p) {
+  p.tlas = S.tlas.data();
+  p.pose = S.pose.data();
+  p.gstat = S.gstat.data();
+  p.plane_ids = S.hm.plane_ids.data();
+  p.mesh = S.meshes.infos.data();
+  p.mnodes = S.meshes.nodes.data();
+  p.mtris = S.meshes.tris.data();
+  p.nnode = (int)S.tlas.size();
+  p.ngeom = S.hm.ngeom;
+  p.nplane = (int)S.hm.plane_ids.size();
+  p.nworld = 1;
+}
+
+void run(const EmuScene& S, CastParams& p, const double o[3], const double* R) {
+  HostWarp warp;
+  HostLd ld;
+  const float tcap = p.mode == MODE_MULTIRAY ? f32_up(p.cutoff) : FLT_MAX;
+  for (int r = 0; r < p.nray; r++) {
+    double l[3], vec[3];
+    const bool active = cast_make_ray(p, p.mode, R, r, l, vec);
+    const Hit hit = trace_ray(p, p.tlas, p.pose, active, o, vec, tcap, warp, ld);
+    cast_epilogue(p, p.mode, 0, r, hit, l);
+  }
+}
+
+}  // namespace
+
+extern "C" {
+
+// mirrors b2_multiray for one world; topo_xpos/topo_xmat (nullable) = poses the BVH topology is
+// built on when different from the poses the rays are cast against
+int emu_multiray(const b2_model_desc* m, const double* xpos, const double* xmat,
+                 const double* topo_xpos, const double* topo_xmat, const double pnt[3],
+                 const double* vec, const uint8_t* geomgroup, uint8_t flg_static, int bodyexclude,
+                 int32_t* geomid, double* dist, int nray, double cutoff, int mesh_leaf) {
+  EmuScene S;
+  std::string err;
+  if (!make_scene(m, xpos, xmat, topo_xpos, topo_xmat, mesh_leaf, S, err)) return -1;
+  std::vector<uint8_t> elim;
+  eliminate_flags(S.hm, geomgroup, flg_static, bodyexclude, elim);
+  elim.push_back(0);
+  CastParams p{};
+  fill_params(S, p);
+  p.elim = elim.data();
+  p.local_dir = vec;
+  p.nray = nray;
+  p.mode = MODE_MULTIRAY;
+  p.cutoff = cutoff;
+  p.nscan = 1;
+  p.geomid = geomid;
+  p.dist = dist;
+  run(S, p, pnt, nullptr);
+  return 0;
+}
+
+// mirrors b2_lidar_cast for one scan in one world
+int emu_lidar(const b2_model_desc* m, const double* xpos, const double* xmat,
+              const b2_lidar_desc* d, const double pos[3], const double mat[9], float* ranges,
+              int32_t* geomid, double* dist, float* xyz, int mesh_leaf) {
+  EmuScene S;
+  std::string err;
+  if (!make_scene(m, xpos, xmat, nullptr, nullptr, mesh_leaf, S, err)) return -1;
+  std::vector<uint8_t> elim;
+  eliminate_flags(S.hm, d->geomgroup, d->flg_static, d->bodyexclude, elim);
+  elim.push_back(0);
+  CastParams p{};
+  fill_params(S, p);
+  p.elim = elim.data();
+  p.local_dir = d->local_dir;
+  p.nray = d->nray;
+  p.mode = MODE_LIDAR;
+  p.cutoff = d->cutoff;
+  p.range_min = d->range_min;
+  p.range_max = d->range_max;
+  p.nscan = 1;
+  p.ranges = ranges;
+  p.geomid = geomid;
+  p.dist = dist;
+  p.xyz = xyz;
+  run(S, p, pos, mat);
+  return 0;
+}
+
+// BVH statistics for tests: node count and max depth of the geom BVH and total mesh nodes
+int emu_bvh_stats(const b2_model_desc* m, const double* xpos, const double* xmat, int mesh_leaf,
+                  int32_t* nnode, int32_t* depth, int64_t* mesh_nodes) {
+  EmuScene S;
+  std::string err;
+  if (!make_scene(m, xpos, xmat, nullptr, nullptr, mesh_leaf, S, err)) return -1;
+  *nnode = (int32_t)S.tlas.size();
+  *depth = S.topo.max_depth;
+  *mesh_nodes = (int64_t)S.meshes.nodes.size();
+  return 0;
+}
+
+}  // extern "C"
