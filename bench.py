@@ -1,0 +1,387 @@
+#!/usr/bin/env python
+"""bench.py -- lidar rays/s (Grays/s) on N B200s next to the mj_multiRay-style oracle on host cores.
+
+Workload (BASELINE.json configs[1]): the clutter500 scene (1 plane + 4 walls +
+primitives + mesh instances, ~500 geoms, seed 20261018) scanned by a 64x2048 3-D lidar from
+`--scans` jittered sensor poses per GPU per step (default 1024 => 1.34e8 rays and 1.07 GB of
+results per launch, far larger than the 126 MB L2).  One step = pose refresh + BVH refit (K1) +
+one cast launch (K2).  Weak scaling: every rank casts its own batch of sensor poses against its
+own replica of the scene; no collective on the data path.
+
+Prints ONE JSON line (rank 0).  `--impl reference` times the CPU oracle (the restatement of
+MuJoCo's mj_multiRay; libmujoco itself is not available in this image) on all host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "lidar_rays_per_s"
+UNIT = "Grays/s"
+N_EL, N_AZ = 64, 2048
+BYTES_PER_RAY = 8  # f32 range + i32 geomid written; rays are generated on-chip
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--scans", type=int, default=1024, help="sensor poses per GPU per step")
+    ap.add_argument("--e2e-scans", type=int, default=256, help="sensor poses per e2e step")
+    ap.add_argument("--ref-scans", type=int, default=4, help="scans per step of the CPU arm")
+    ap.add_argument("--cpu-baseline-scans", type=int, default=24)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true")
+    ap.add_argument("--gather", action="store_true", help="also time an NCCL all-gather of results")
+    return ap.parse_args()
+
+
+def env_rank():
+    return (int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)),
+            int(os.environ.get("WORLD_SIZE", 1)))
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured"
+        except Exception:
+            pass
+    return 6650.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons while the timed region runs (B200_PROFILING.md)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.rows = []
+        self.stop = threading.Event()
+        self.t = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        while not self.stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                      "-i", str(self.index)], capture_output=True, text=True, timeout=5).stdout
+                for line in out.strip().splitlines():
+                    self.rows.append([x.strip() for x in line.split(",")])
+            except Exception:
+                pass
+            self.stop.wait(0.2)
+
+    def __enter__(self):
+        self.t.start()
+        return self
+
+    def __exit__(self, *a):
+        self.stop.set()
+        self.t.join(timeout=6)
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx.append(float(r[2]))
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown",
+                                    "sw_power_cap"), r[4:8]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                continue
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def cpu_arm(scene_np, nscan: int, nthread: int, seed_off: int = 0):
+    """Oracle (mj_multiRay restatement) on `nscan` full scans; returns (rays, seconds)."""
+    from oracle import binding as orc
+    oc = orc.OracleScene(scene_np.model, scene_np.poses)
+    pos, mat = scene_np.sensor_poses(nscan, seed=20261018 + 1 + seed_off)
+    t0 = time.perf_counter()
+    for i in range(nscan):
+        oc.lidar_scan(scene_np.lidar, pos[i], mat[i], nthread=nthread)
+    return nscan * scene_np.lidar.nray, time.perf_counter() - t0
+
+
+def run_reference(args):
+    rank, _, world = env_rank()
+    if rank != 0:
+        return
+    from mujoco_ros2_simulation_b200 import scenes
+    from oracle import binding as orc
+    orc.build()
+    cs = scenes.clutter500(n_el=N_EL, n_az=N_AZ)
+    cores = os.cpu_count() or 1
+    for w in range(args.warmup):
+        cpu_arm(cs, 1, cores, w)
+    t0 = time.perf_counter()
+    rays = 0
+    for k in range(args.steps):
+        r, _ = cpu_arm(cs, args.ref_scans, cores, 100 + k)
+        rays += r
+    dt = time.perf_counter() - t0
+    val = rays / dt / 1e9
+    sample = f"{args.ref_scans} scans x {cs.lidar.nray} rays per step on the same scene"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": f"clutter500 (~500 geoms, meshes) 64x2048 lidar, {args.ref_scans} scans/step",
+                   "note": "CPU oracle = C restatement of MuJoCo 3.3.4 mj_multiRay (libmujoco absent)"},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+
+    from mujoco_ros2_simulation_b200 import engine, scenes
+
+    rank, local_rank, world = env_rank()
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device: the engine has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+
+    cs = scenes.clutter500(n_el=N_EL, n_az=N_AZ)
+    nray = cs.lidar.nray
+    stream = torch.cuda.Stream(device=dev)
+    scene = engine.Scene(cs.model, nworld=1, device=local_rank, stream=stream.cuda_stream)
+    scene.update_poses(cs.poses)
+    lidar = engine.Lidar(scene, cs.lidar)
+    nscan = args.scans
+    pos, mat = cs.sensor_poses(nscan, seed=20261018 + 1 + 7919 * rank)
+    with torch.cuda.stream(stream):
+        d_pos = torch.from_numpy(pos).to(dev)
+        d_mat = torch.from_numpy(mat).to(dev)
+        d_world = torch.zeros(nscan, dtype=torch.int32, device=dev)
+        d_xpos = torch.from_numpy(cs.poses.geom_xpos).to(dev)
+        d_xmat = torch.from_numpy(cs.poses.geom_xmat).to(dev)
+        ranges = torch.empty((nscan, nray), dtype=torch.float32, device=dev)
+        geomid = torch.empty((nscan, nray), dtype=torch.int32, device=dev)
+    stream.synchronize()
+
+    def step(ev0=None, ev1=None):
+        scene.update_poses_device(d_xpos, d_xmat)  # K1: pose refresh + refit, every step
+        if ev0 is not None:
+            ev0.record(stream)
+        lidar.cast_device(nscan, d_pos, d_mat, d_world, ranges=ranges, geomid=geomid)  # K2
+        if ev1 is not None:
+            ev1.record(stream)
+
+    with torch.cuda.stream(stream):
+        for _ in range(max(args.warmup, 3)):
+            step()
+        stream.synchronize()
+        torch.cuda.synchronize()
+        barrier()
+        kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+               for _ in range(args.steps)]
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = engine.launch_count()
+        with ClockSampler(local_rank) as clk:
+            e0.record(stream)
+            for k in range(args.steps):
+                step(*kev[k])
+            e1.record(stream)
+            stream.synchronize()
+            torch.cuda.synchronize()
+        launches = engine.launch_count() - l0
+        barrier()
+    ms_total = e0.elapsed_time(e1)
+    ms_kernel = float(np.mean([a.elapsed_time(b) for a, b in kev]))
+    t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total_max = float(t.item())
+    rays_per_step = nscan * nray
+    value = world * rays_per_step * args.steps / (ms_total_max * 1e-3) / 1e9
+
+    # sanity on the result of the last step (not timed): hit fraction of this scene is ~0.99
+    hit_frac = float((geomid[0] >= 0).float().mean().item())
+
+    # ---- e2e: host buffers through the blocking C-ABI call, copies inside the timed region ------
+    es = min(args.e2e_scans, nscan)
+    h_pos = torch.from_numpy(pos[:es].copy()).pin_memory()
+    h_mat = torch.from_numpy(mat[:es].copy()).pin_memory()
+    h_world = torch.zeros(es, dtype=torch.int32).pin_memory()
+    h_ranges = torch.empty((es, nray), dtype=torch.float32).pin_memory()
+    h_geomid = torch.empty((es, nray), dtype=torch.int32).pin_memory()
+    h_xpos = torch.from_numpy(cs.poses.geom_xpos.copy()).pin_memory()
+    h_xmat = torch.from_numpy(cs.poses.geom_xmat.copy()).pin_memory()
+    lib = scene.lib
+
+    def e2e_step():
+        engine._capi.check(lib.b2_scene_update_poses(scene._h, 0, 1, h_xpos.data_ptr(), h_xmat.data_ptr()))
+        engine._capi.check(lib.b2_lidar_cast(lidar._h, es, h_world.data_ptr(), h_pos.data_ptr(),
+                                             h_mat.data_ptr(), h_ranges.data_ptr(), h_geomid.data_ptr(),
+                                             None, None))
+
+    for _ in range(2):
+        e2e_step()
+    torch.cuda.synchronize()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        e2e_step()
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    t = torch.tensor([dt], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_val = world * es * nray * args.steps / float(t.item()) / 1e9
+    h2d = es * (3 + 9) * 8 + es * 4 + int(h_xpos.numel() + h_xmat.numel()) * 8
+    d2h = es * nray * BYTES_PER_RAY
+    e2e_ok = bool((h_geomid[0].numpy() == geomid[0].cpu().numpy()).all()) if es > 0 else True
+
+    # ---- optional: gather of the results over NVLink (not on the data path) -------------------------
+    gather_ms = None
+    if args.gather and world > 1:
+        g_r = torch.empty((world,) + tuple(ranges.shape), dtype=ranges.dtype, device=dev)
+        g_g = torch.empty((world,) + tuple(geomid.shape), dtype=geomid.dtype, device=dev)
+        for _ in range(2):
+            dist.all_gather_into_tensor(g_r, ranges)
+            dist.all_gather_into_tensor(g_g, geomid)
+        torch.cuda.synchronize()
+        barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        dist.all_gather_into_tensor(g_r, ranges)
+        dist.all_gather_into_tensor(g_g, geomid)
+        b.record()
+        torch.cuda.synchronize()
+        t = torch.tensor([a.elapsed_time(b)], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        gather_ms = float(t.item())
+        del g_r, g_g
+
+    # ---- secondary: K3 depth -> cloud (the genuinely HBM-bound kernel), cfg4 shape ---------------------
+    secondary = None
+    if not args.no_secondary and rank == 0:
+        ncam = 256
+        cam = engine.DepthCamera(scenes.depth_camera(), scene=scene, device=local_rank)
+        with torch.cuda.stream(stream):
+            gl = torch.rand((ncam, 480, 640), dtype=torch.float32, device=dev)
+            dimg = torch.empty_like(gl)
+            cloud = torch.empty((ncam, 480, 640, 3), dtype=torch.float32, device=dev)
+            for _ in range(3):
+                cam.depth_to_cloud_device(ncam, gl, dimg, cloud)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(stream)
+            reps = 10
+            for _ in range(reps):
+                cam.depth_to_cloud_device(ncam, gl, dimg, cloud)
+            b.record(stream)
+            stream.synchronize()
+        ms = a.elapsed_time(b) / reps
+        npx = ncam * 480 * 640
+        peak, how = measured_peak()
+        gbs = npx * 20 / (ms * 1e-3) / 1e9
+        secondary = {"kernel": "depth_to_cloud", "workload": f"{ncam} x 640x480 depth -> 32FC1 + xyz (point_step 12)",
+                     "gpx_per_s": npx / (ms * 1e-3) / 1e9, "ms": ms,
+                     "roofline": {"bound": "hbm", "achieved": gbs, "peak": peak, "unit": "GB/s",
+                                  "frac": gbs / peak, "bytes_per_px": 20, "peak_source": how}}
+        del gl, dimg, cloud
+        cam.close()
+
+    # ---- roofline of the dominant kernel (K2 cast) ------------------------------------------------------
+    st = scene.stats()
+    scene_bytes = cs.model.ngeom * (32 + 96) + st["bvh_nodes"] * 64 + st["mesh_nodes"] * 64 + st["mesh_tris"] * 48
+    alg_bytes = BYTES_PER_RAY * rays_per_step + scene_bytes
+    peak, how = measured_peak()
+    achieved = alg_bytes / (ms_kernel * 1e-3) / 1e9
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tp):
+        try:
+            traffic = json.load(open(tp)).get("cast_kernel_dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+
+    # ---- CPU baseline (rank 0, N=1): the oracle on a bounded sample of the same workload -------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        from oracle import binding as orc
+        orc.build()
+        cores = os.cpu_count() or 1
+        cpu_arm(cs, 1, cores)
+        rays, secs = cpu_arm(cs, args.cpu_baseline_scans, cores, 50)
+        cpu = {"value": rays / secs / 1e9, "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": f"{args.cpu_baseline_scans} of the {nscan} scans ({rays} rays), oracle "
+                         "(C restatement of mj_multiRay, -O3) on all host cores"}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_total_max / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic",
+            "config": {
+                "workload": f"clutter500 ({cs.model.ngeom} geoms incl. {int((cs.model.geom_type == 7).sum())} "
+                            f"mesh instances, {cs.model.nface} unique triangles) 64x2048 3-D lidar x {nscan} "
+                            "sensor poses per GPU per step; pose refresh + BVH refit every step",
+                "rays_per_step_per_gpu": rays_per_step, "l2": "outputs 1.07 GB per launch > 126 MB L2",
+                "parallelism": f"replica x{world}, sensor-pose batches sharded, no data-path collective",
+                "gather_ms": gather_ms, "hit_fraction": hit_frac, "e2e_matches_device_path": e2e_ok,
+                "bvh_nodes": st["bvh_nodes"], "mesh_nodes": st["mesh_nodes"],
+            },
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": traffic, "kernel": "cast_kernel<LIDAR>",
+                         "kernel_ms": ms_kernel, "algorithmic_bytes_per_launch": alg_bytes,
+                         "peak_source": how,
+                         "note": "ray casting is traversal/FP64-issue bound, not HBM bound (SURVEY.md M3)"},
+            "cpu_baseline": cpu,
+            "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "scans_per_step": es},
+            "gpu_launches": int(launches),
+            "clocks": clk.summary(),
+            "secondary": secondary,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,130 @@
+"""CPU tier: the product's traversal code (csrc/ray_core.cuh + scene_build/bvh_build), compiled for
+the host by tests/emu with a 1-lane warp, against the oracle -- bit-exact distances and geom ids.
+This checks the LOGIC that runs on the B200 (BVH build, refit boxes, conservative fp32 culling,
+packet traversal control flow, deferred mesh candidates, tie rule, epilogues) before any GPU time
+is spent; the GPU tier (test_gpu_parity.py) repeats it through the C ABI on the device."""
+import numpy as np
+import pytest
+
+from mujoco_ros2_simulation_b200 import scenes
+from mujoco_ros2_simulation_b200.model import GEOM_MESH
+
+
+@pytest.fixture(scope="module")
+def clutter():
+    return scenes.clutter500(n_el=32, n_az=256)
+
+
+def test_emu_test_robot(oracle, emu):
+    rs = scenes.robot_scene()
+    o = oracle.OracleScene(rs.model, rs.poses)
+    r, g, raw = o.lidar_scan(rs.lidar, rs.lidar_pos, rs.lidar_mat)
+    r2, g2, raw2, xyz = emu.lidar(rs.model, rs.poses, rs.lidar, rs.lidar_pos, rs.lidar_mat)
+    assert np.array_equal(r, r2) and np.array_equal(g, g2) and np.array_equal(raw, raw2)
+    assert g2.tolist() == [0] * 13 + [2] * 11          # ties: collision box wins over visual copy
+    ref_xyz = (rs.lidar.local_dir * raw[:, None]).astype(np.float32)
+    assert np.array_equal(xyz, ref_xyz)
+    rs360 = scenes.robot_scene(360)                    # cfg1
+    r, g, raw = o.lidar_scan(rs360.lidar, rs360.lidar_pos, rs360.lidar_mat)
+    r2, g2, raw2, xyz = emu.lidar(rs360.model, rs360.poses, rs360.lidar, rs360.lidar_pos, rs360.lidar_mat)
+    assert np.array_equal(r, r2) and np.array_equal(g, g2) and np.array_equal(raw, raw2)
+    assert (g >= 0).sum() > 30 and (r == -1).sum() > 200
+    assert np.isnan(xyz[r2 == -1]).all()
+
+
+@pytest.mark.parametrize("gg,fs", [(None, 1), ([1, 0, 1, 1, 0, 0], 1), (None, 0), ([1, 0, 1, 1, 0, 0], 0)])
+def test_emu_clutter_masks(oracle, emu, clutter, gg, fs):
+    cs = clutter
+    o = oracle.OracleScene(cs.model, cs.poses)
+    vec = cs.lidar.local_dir
+    d, g = o.multi_ray(cs.sensor_pos, vec, geomgroup=gg, flg_static=fs, bodyexclude=63, nthread=4)
+    d2, g2 = emu.multiray(cs.model, cs.poses, cs.sensor_pos, vec, geomgroup=gg, flg_static=fs,
+                          bodyexclude=63)
+    assert np.array_equal(d, d2)
+    assert np.array_equal(g, g2)
+    assert (cs.model.geom_type[g[g >= 0]] == GEOM_MESH).sum() > 50 or fs == 0
+
+
+def test_emu_ties_resolved_to_lowest_id(oracle, emu, clutter):
+    """every 10th clutter geom has a coincident copy with the next id: it must never be reported."""
+    cs = clutter
+    m = cs.model
+    dup = np.zeros(m.ngeom, bool)
+    for i in range(1, m.ngeom):
+        dup[i] = (m.geom_type[i] == m.geom_type[i - 1]
+                  and np.array_equal(cs.poses.geom_xpos[0, i], cs.poses.geom_xpos[0, i - 1])
+                  and m.geom_group[i] == m.geom_group[i - 1])
+    assert dup.sum() > 20
+    d2, g2 = emu.multiray(m, cs.poses, cs.sensor_pos, cs.lidar.local_dir, bodyexclude=63)
+    hit = g2[g2 >= 0]
+    assert not dup[hit].any()
+    assert dup[hit + 1 - (hit + 1 >= m.ngeom)].any()   # the originals of some duplicates are hit
+
+
+def test_emu_bodyexclude_matters(oracle, emu, clutter):
+    cs = clutter
+    d_in, g_in = emu.multiray(cs.model, cs.poses, cs.sensor_pos, cs.lidar.local_dir[::9], bodyexclude=-1)
+    assert np.isin(g_in, np.nonzero(cs.model.geom_bodyid == 63)[0]).all()   # housing hit from inside
+    o = oracle.OracleScene(cs.model, cs.poses)
+    d, g = o.multi_ray(cs.sensor_pos, cs.lidar.local_dir[::9], bodyexclude=-1)
+    assert np.array_equal(d, d_in) and np.array_equal(g, g_in)
+
+
+def test_emu_refit_world_with_foreign_topology(oracle, emu, clutter):
+    """S5: BVH topology built on world 0, boxes refit to a jittered world."""
+    cs = clutter
+    P = scenes.clutter_worlds(cs, 3)
+    o = oracle.OracleScene(cs.model, P, world=2)
+    vec = cs.lidar.local_dir[::3]
+    d, g = o.multi_ray(cs.sensor_pos, vec, bodyexclude=63, nthread=4)
+    d2, g2 = emu.multiray(cs.model, P, cs.sensor_pos, vec, bodyexclude=63, world=2, topo_world=0)
+    assert np.array_equal(d, d2) and np.array_equal(g, g2)
+
+
+def test_emu_jittered_sensor_and_cutoff(oracle, emu, clutter):
+    cs = clutter
+    pos, mat = cs.sensor_poses(3)
+    o = oracle.OracleScene(cs.model, cs.poses)
+    spec = scenes.LidarSpec(cs.lidar.local_dir, bodyexclude=63, cutoff=12.0, range_min=1.0, range_max=11.0)
+    for i in (1, 2):
+        r, g, raw = o.lidar_scan(spec, pos[i], mat[i], nthread=4)
+        r2, g2, raw2, _ = emu.lidar(cs.model, cs.poses, spec, pos[i], mat[i])
+        assert np.array_equal(r, r2) and np.array_equal(g, g2) and np.array_equal(raw, raw2)
+        assert (r == -1).any() and (raw == 12.0).any()
+    d, g = o.multi_ray(pos[1], cs.lidar.local_dir[::5], bodyexclude=63, cutoff=6.0)
+    d2, g2 = emu.multiray(cs.model, cs.poses, pos[1], cs.lidar.local_dir[::5], bodyexclude=63, cutoff=6.0)
+    assert np.array_equal(d, d2) and np.array_equal(g, g2)
+
+
+def test_emu_arm_worlds(oracle, emu):
+    ws = scenes.arm_worlds(nworld=6, n_rays=256)
+    for w in range(6):
+        o = oracle.OracleScene(ws.model, ws.poses, world=w)
+        r, g, raw = o.lidar_scan(ws.lidar, ws.sensor_pos[w], ws.sensor_mat[w])
+        r2, g2, raw2, _ = emu.lidar(ws.model, ws.poses, ws.lidar, ws.sensor_pos[w], ws.sensor_mat[w], world=w)
+        assert np.array_equal(r, r2) and np.array_equal(g, g2) and np.array_equal(raw, raw2)
+    assert (g == 0).any()   # the tilted scan plane reaches the ground plane
+
+
+def test_emu_degenerate_inputs(oracle, emu, clutter):
+    cs = clutter
+    vec = np.array([[0, 0, 0.0], [1e-20, 0, 0], [0, 0, -1.0], [1, 0, 0], [0, 1, 0], [0, 0, 1.0],
+                    [1e-9, 0, -1.0], [3.0, 4.0, 0.0]])
+    o = oracle.OracleScene(cs.model, cs.poses)
+    d, g = o.multi_ray(cs.sensor_pos, vec, bodyexclude=63)
+    d2, g2 = emu.multiray(cs.model, cs.poses, cs.sensor_pos, vec, bodyexclude=63)
+    assert np.array_equal(d, d2) and np.array_equal(g, g2)
+    assert d[0] == -1 and g[0] == -1 and d[2] == 1.5 and g[2] == 0      # straight down: plane at 1.5
+    assert abs(d[7] * 5.0 - d[3] * 1.0) < 30                            # non-unit vec: units of |vec|
+    # empty ray list
+    d3, g3 = emu.multiray(cs.model, cs.poses, cs.sensor_pos, np.zeros((0, 3)), bodyexclude=63)
+    assert d3.shape == (0,)
+
+
+def test_emu_mesh_leaf_sizes_agree(emu, clutter):
+    cs = clutter
+    vec = cs.lidar.local_dir[::2]
+    ref = emu.multiray(cs.model, cs.poses, cs.sensor_pos, vec, bodyexclude=63, mesh_leaf=1)
+    for leaf in (2, 4):
+        out = emu.multiray(cs.model, cs.poses, cs.sensor_pos, vec, bodyexclude=63, mesh_leaf=leaf)
+        assert np.array_equal(ref[0], out[0]) and np.array_equal(ref[1], out[1])
