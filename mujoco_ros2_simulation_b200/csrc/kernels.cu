@@ -88,76 +88,56 @@ cudaError_t launch_refit(const RefitParams& p, cudaStream_t stream) {
 // =============================================================================================
 // K2: cast
 // =============================================================================================
+// per-warp shared-memory scratch of the cast kernel
+struct WarpScratch {
+  F4 cand_a[kCandCap];          // candidate box lo.xyz + distance key
+  F4 cand_b[kCandCap];          // candidate box hi.xyz + geom id bits
+  int32_t queue[kQueueCap];     // collect frontier
+  int32_t order[kCandCap];      // rank-sorted candidate slots
+  int32_t stack[kPacketStack];  // fallback packet traversal
+};
+
 struct DevWarp {
-  int32_t* stack;  // this warp's slice of shared memory
-  int lane;
+  WarpScratch* s;
+  int lane_;
+  __device__ __forceinline__ int size() const { return 32; }
+  __device__ __forceinline__ int lane() const { return lane_; }
+  __device__ __forceinline__ unsigned lanemask_lt() const { return (1u << lane_) - 1u; }
   __device__ __forceinline__ unsigned ballot(bool pred) const {
     return __ballot_sync(0xffffffffu, pred);
   }
+  __device__ __forceinline__ bool any(bool pred) const { return __any_sync(0xffffffffu, pred); }
   __device__ __forceinline__ int popc(unsigned m) const { return __popc(m); }
+  __device__ __forceinline__ void sync() const { __syncwarp(); }
+  __device__ __forceinline__ float sum(float v) const {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+  }
+  __device__ __forceinline__ float min(float v) const {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fminf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+  }
+  __device__ __forceinline__ float max(float v) const {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+  }
+  __device__ __forceinline__ int32_t* queue() const { return s->queue; }
+  __device__ __forceinline__ F4* cand_a() const { return s->cand_a; }
+  __device__ __forceinline__ F4* cand_b() const { return s->cand_b; }
+  __device__ __forceinline__ int32_t* order() const { return s->order; }
   __device__ __forceinline__ void push(int& sp, int32_t v) {
     if (sp < kPacketStack) {
-      if (lane == 0) stack[sp] = v;
+      if (lane_ == 0) s->stack[sp] = v;
       sp++;
     }
     __syncwarp();
   }
   __device__ __forceinline__ int32_t pop(int& sp) {
     --sp;
-    return stack[sp];
-  }
-};
-
-template <bool STAGE>
-struct DevLd {
-  static __device__ __forceinline__ BvhNode load_ro(const BvhNode* ptr) {
-    BvhNode n;
-    const float4* q = reinterpret_cast<const float4*>(ptr);
-    float4* o = reinterpret_cast<float4*>(&n);
-    o[0] = __ldg(q);
-    o[1] = __ldg(q + 1);
-    o[2] = __ldg(q + 2);
-    o[3] = __ldg(q + 3);
-    return n;
-  }
-  __device__ __forceinline__ BvhNode node(const BvhNode* ptr) const { return load_ro(ptr); }
-  __device__ __forceinline__ BvhNode tlas_node(const BvhNode* ptr) const {
-    if (STAGE) {
-      BvhNode n;
-      const float4* q = reinterpret_cast<const float4*>(ptr);  // shared memory
-      float4* o = reinterpret_cast<float4*>(&n);
-      o[0] = q[0];
-      o[1] = q[1];
-      o[2] = q[2];
-      o[3] = q[3];
-      return n;
-    }
-    return load_ro(ptr);
-  }
-  __device__ __forceinline__ MeshTri tri(const MeshTri* ptr) const {
-    MeshTri t;
-    const float4* q = reinterpret_cast<const float4*>(ptr);
-    float4* o = reinterpret_cast<float4*>(&t);
-    o[0] = __ldg(q);
-    o[1] = __ldg(q + 1);
-    o[2] = __ldg(q + 2);
-    return t;
-  }
-  __device__ __forceinline__ GeomPose pose(const GeomPose* ptr) const {
-    GeomPose P;
-    const double2* q = reinterpret_cast<const double2*>(ptr);
-    double2* o = reinterpret_cast<double2*>(&P);
-#pragma unroll
-    for (int i = 0; i < 6; i++) o[i] = __ldg(q + i);
-    return P;
-  }
-  __device__ __forceinline__ GeomStatic gstat(const GeomStatic* ptr) const {
-    GeomStatic g;
-    const double2* q = reinterpret_cast<const double2*>(ptr);
-    double2* o = reinterpret_cast<double2*>(&g);
-    o[0] = __ldg(q);
-    o[1] = __ldg(q + 1);
-    return g;
+    return s->stack[sp];
   }
 };
 
@@ -175,8 +155,8 @@ __global__ void __launch_bounds__(kCastThreads)
     cast_kernel(const __grid_constant__ CastParams p, const int tiles_per_block,
                 const int tiles_per_scan, const int chunks_per_scan, const int tiles_x) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  int32_t* stacks = reinterpret_cast<int32_t*>(smem_raw);
-  BvhNode* s_tlas = reinterpret_cast<BvhNode*>(smem_raw + kCastWarps * kPacketStack * sizeof(int32_t));
+  WarpScratch* scratch = reinterpret_cast<WarpScratch*>(smem_raw);
+  BvhNode* s_tlas = reinterpret_cast<BvhNode*>(smem_raw + kCastWarps * sizeof(WarpScratch));
 
   const int warp_id = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int scan = blockIdx.x / chunks_per_scan;
@@ -202,8 +182,7 @@ __global__ void __launch_bounds__(kCastThreads)
     for (int k = 0; k < 9; k++) R[k] = __ldg(p.smat + (size_t)scan * 9 + k);
   }
 
-  DevWarp warp{stacks + warp_id * kPacketStack, lane};
-  const DevLd<STAGE> ld;
+  DevWarp warp{scratch + warp_id, lane};
   const float tcap = (MODE == MODE_MULTIRAY) ? f32_up(p.cutoff) : FLT_MAX;
 
   for (int t = warp_id; t < tiles_per_block; t += kCastWarps) {
@@ -216,7 +195,7 @@ __global__ void __launch_bounds__(kCastThreads)
     double l[3], vec[3];
     active = cast_make_ray(p, MODE, R, rr, l, vec) && active;
 
-    const Hit hit = trace_ray(p, tlas, pose, active, o, vec, tcap, warp, ld);
+    const Hit hit = trace_tile<STAGE>(p, tlas, pose, active, o, vec, tcap, warp);
 
     if (r < p.nray) cast_epilogue(p, MODE, scan, r, hit, l);
   }
@@ -240,7 +219,7 @@ static cudaError_t launch_cast_mode(const CastParams& p, bool stage, int tiles_p
   const long long nblocks = (long long)p.nscan * chunks_per_scan;
   if (nblocks <= 0) return cudaSuccess;
   if (nblocks > 0x7fffffffLL) return cudaErrorInvalidConfiguration;
-  size_t smem = kCastWarps * kPacketStack * sizeof(int32_t);
+  size_t smem = kCastWarps * sizeof(WarpScratch);
   if (stage) smem += (size_t)p.nnode * sizeof(BvhNode);
   cudaError_t err;
   if (stage) {

@@ -9,13 +9,26 @@
 // Numerics: every accepted hit distance is computed in IEEE double with the operation order of
 // MuJoCo 3.3.4 engine_ray.c, compiled with FMA contraction OFF
 // (nvcc -fmad=false), so distances are bit-identical to the CPU oracle.  fp32 is used only for
-// conservative culling (slab tests against outward-rounded boxes) and can never drop a hit the
-// double test would accept.
+// conservative culling (tile cone vs box, slab tests against outward-rounded boxes) and can never
+// drop a hit the double test would accept.
+//
+// Traversal (one warp = one tile of 32 rays that share an origin):
+//   1. planes (kept outside the BVH) are tested first: they bound the search distance;
+//   2. COLLECT: the warp walks the geom BVH once for the whole tile -- each lane tests a different
+//      node's two child boxes against the tile's bounding cone and against the farthest distance
+//      any lane still needs -- and gathers the surviving geoms into a shared-memory candidate list;
+//   3. candidates are rank-sorted by their distance from the origin and visited in that order by
+//      all lanes together: per-lane conservative slab test, then the closed-form fp64 test of the
+//      (warp-uniform) geom type; the loop ends as soon as no lane can still improve;
+//   4. mesh geoms a lane's ray enters are deferred and traced per lane through the mesh BVH;
+//   5. tiles whose candidate set does not fit (incoherent rays) fall back to a per-node packet
+//      traversal with a shared stack.
 #ifndef B2_RAY_CORE_CUH
 #define B2_RAY_CORE_CUH
 
 #include <float.h>
 #include <math.h>
+#include <string.h>
 
 #include "b2_types.h"
 
@@ -26,13 +39,45 @@ namespace b2 {
 #else
 #define B2_ON_DEVICE 0
 #endif
+// heavy leaf routines: one out-of-line copy on the device keeps the kernel's hot loops inside the
+// instruction cache (the fully inlined first version was 140 KB of SASS and stalled on fetch)
+#if defined(__CUDACC__)
+#define B2_LEAF static __host__ __device__ __noinline__
+#else
+#define B2_LEAF static inline
+#endif
 
-constexpr int kPacketStack = 64;  // geom-BVH stack entries per warp
+constexpr int kPacketStack = 64;  // geom-BVH stack entries per warp (fallback traversal)
 constexpr int kMeshStack = 64;    // mesh-BVH stack entries per lane
 constexpr int kMaxMeshCand = 12;  // deferred mesh candidates per lane
+constexpr int kQueueCap = 96;     // collect frontier (node ids) per warp
+constexpr int kCandCap = 64;      // candidate geoms per tile
+
+struct B2_ALIGN(16) F4 {
+  float x, y, z, w;
+};
+
+B2_HD float int_as_f32(int32_t i) {
+#if B2_ON_DEVICE
+  return __int_as_float(i);
+#else
+  float f;
+  memcpy(&f, &i, 4);
+  return f;
+#endif
+}
+B2_HD int32_t f32_as_int(float f) {
+#if B2_ON_DEVICE
+  return __float_as_int(f);
+#else
+  int32_t i;
+  memcpy(&i, &f, 4);
+  return i;
+#endif
+}
 
 // ---------------------------------------------------------------------------------------------
-// directed rounding double -> float
+// directed rounding
 // ---------------------------------------------------------------------------------------------
 B2_HD float f32_up(double x) {
 #if B2_ON_DEVICE
@@ -50,6 +95,113 @@ B2_HD float f32_down(double x) {
   float f = (float)x;
   if ((double)f > x) f = nextafterf(f, -INFINITY);
   return f;
+#endif
+}
+B2_HD float fmul_up(float a, float b) {
+#if B2_ON_DEVICE
+  return __fmul_ru(a, b);
+#else
+  return f32_up((double)a * (double)b);  // the double product of two floats is exact
+#endif
+}
+B2_HD float fmul_down(float a, float b) {
+#if B2_ON_DEVICE
+  return __fmul_rd(a, b);
+#else
+  return f32_down((double)a * (double)b);
+#endif
+}
+B2_HD float fma_rn(float a, float b, float c) {
+#if B2_ON_DEVICE
+  return __fmaf_rn(a, b, c);
+#else
+  return fmaf(a, b, c);
+#endif
+}
+
+// ---------------------------------------------------------------------------------------------
+// read-only loads of scene records
+// ---------------------------------------------------------------------------------------------
+B2_HD BvhNode ld_node(const BvhNode* ptr) {
+#if B2_ON_DEVICE
+  BvhNode n;
+  const float4* q = reinterpret_cast<const float4*>(ptr);
+  float4* o = reinterpret_cast<float4*>(&n);
+  o[0] = __ldg(q);
+  o[1] = __ldg(q + 1);
+  o[2] = __ldg(q + 2);
+  o[3] = __ldg(q + 3);
+  return n;
+#else
+  return *ptr;
+#endif
+}
+// geom-BVH node: shared memory when staged (generic load), else the read-only path
+template <bool STAGE>
+B2_HD BvhNode ld_tlas(const BvhNode* ptr) {
+#if B2_ON_DEVICE
+  if (STAGE) {
+    BvhNode n;
+    const float4* q = reinterpret_cast<const float4*>(ptr);
+    float4* o = reinterpret_cast<float4*>(&n);
+    o[0] = q[0];
+    o[1] = q[1];
+    o[2] = q[2];
+    o[3] = q[3];
+    return n;
+  }
+#endif
+  return ld_node(ptr);
+}
+B2_HD MeshTri ld_tri(const MeshTri* ptr) {
+#if B2_ON_DEVICE
+  MeshTri t;
+  const float4* q = reinterpret_cast<const float4*>(ptr);
+  float4* o = reinterpret_cast<float4*>(&t);
+  o[0] = __ldg(q);
+  o[1] = __ldg(q + 1);
+  o[2] = __ldg(q + 2);
+  return t;
+#else
+  return *ptr;
+#endif
+}
+B2_HD GeomPose ld_pose(const GeomPose* ptr) {
+#if B2_ON_DEVICE
+  GeomPose P;
+  const double2* q = reinterpret_cast<const double2*>(ptr);
+  double2* o = reinterpret_cast<double2*>(&P);
+#pragma unroll
+  for (int i = 0; i < 6; i++) o[i] = __ldg(q + i);
+  return P;
+#else
+  return *ptr;
+#endif
+}
+B2_HD GeomStatic ld_gstat(const GeomStatic* ptr) {
+#if B2_ON_DEVICE
+  GeomStatic g;
+  const double2* q = reinterpret_cast<const double2*>(ptr);
+  double2* o = reinterpret_cast<double2*>(&g);
+  o[0] = __ldg(q);
+  o[1] = __ldg(q + 1);
+  return g;
+#else
+  return *ptr;
+#endif
+}
+B2_HD int32_t ld_geom_type(const GeomStatic* ptr) {
+#if B2_ON_DEVICE
+  return __ldg(&ptr->type);
+#else
+  return ptr->type;
+#endif
+}
+B2_HD uint8_t ld_u8(const uint8_t* ptr) {
+#if B2_ON_DEVICE
+  return __ldg(ptr);
+#else
+  return *ptr;
 #endif
 }
 
@@ -97,10 +249,13 @@ B2_HD double ray_sphere(const double pos[3], double dist_sqr, const double pnt[3
   return ray_quad(a, b, c, x0, x1);
 }
 
-B2_HD double ray_plane(const GeomPose& P, const double size[3], const double pnt[3],
-                       const double vec[3]) {
-  double lpnt[3], lvec[3];
-  ray_map(P, pnt, vec, lpnt, lvec);
+B2_HD void keep_min(double& x, double sol) {
+  if (x < 0 || sol < x) x = sol;
+}
+
+// local-frame parts of the tests (after ray_map and, where upstream has one, the bounding-sphere
+// pre-test)
+B2_HD double local_plane(const double size[3], const double lpnt[3], const double lvec[3]) {
   if (lvec[2] > -kMinVal) return -1;
   const double x = -lpnt[2] / lvec[2];
   if (x < 0) return -1;
@@ -110,16 +265,7 @@ B2_HD double ray_plane(const GeomPose& P, const double size[3], const double pnt
   return -1;
 }
 
-B2_HD void keep_min(double& x, double sol) {
-  if (x < 0 || sol < x) x = sol;
-}
-
-B2_HD double ray_capsule(const GeomPose& P, const double size[3], const double pnt[3],
-                         const double vec[3]) {
-  const double ssz = size[0] + size[1];
-  if (ray_sphere(P.pos, ssz * ssz, pnt, vec) < 0) return -1;
-  double lpnt[3], lvec[3];
-  ray_map(P, pnt, vec, lpnt, lvec);
+B2_HD double local_capsule(const double size[3], const double lpnt[3], const double lvec[3]) {
   double x = -1, x0, x1;
   const double sq_size0 = size[0] * size[0];
   // round side
@@ -128,28 +274,22 @@ B2_HD double ray_capsule(const GeomPose& P, const double size[3], const double p
   double c = lpnt[0] * lpnt[0] + lpnt[1] * lpnt[1] - sq_size0;
   const double sol = ray_quad(a, b, c, x0, x1);
   if (sol >= 0 && fabs(lpnt[2] + sol * lvec[2]) <= size[1]) keep_min(x, sol);
-  // top cap
-  double ldif[3] = {lpnt[0], lpnt[1], lpnt[2] - size[1]};
   a += lvec[2] * lvec[2];
-  b = dot3(lvec, ldif);
-  c = dot3(ldif, ldif) - sq_size0;
-  ray_quad(a, b, c, x0, x1);
-  if (x0 >= 0 && lpnt[2] + x0 * lvec[2] >= size[1]) keep_min(x, x0);
-  if (x1 >= 0 && lpnt[2] + x1 * lvec[2] >= size[1]) keep_min(x, x1);
-  // bottom cap
-  ldif[2] = lpnt[2] + size[1];
-  b = dot3(lvec, ldif);
-  c = dot3(ldif, ldif) - sq_size0;
-  ray_quad(a, b, c, x0, x1);
-  if (x0 >= 0 && lpnt[2] + x0 * lvec[2] <= -size[1]) keep_min(x, x0);
-  if (x1 >= 0 && lpnt[2] + x1 * lvec[2] <= -size[1]) keep_min(x, x1);
+  // caps: side = +1 top (accept z >= size1), side = -1 bottom (accept z <= -size1)
+#pragma unroll 1
+  for (int side = 1; side >= -1; side -= 2) {
+    const double ldif[3] = {lpnt[0], lpnt[1], side > 0 ? lpnt[2] - size[1] : lpnt[2] + size[1]};
+    b = dot3(lvec, ldif);
+    c = dot3(ldif, ldif) - sq_size0;
+    ray_quad(a, b, c, x0, x1);
+    const double z0 = lpnt[2] + x0 * lvec[2], z1 = lpnt[2] + x1 * lvec[2];
+    if (x0 >= 0 && (side > 0 ? z0 >= size[1] : z0 <= -size[1])) keep_min(x, x0);
+    if (x1 >= 0 && (side > 0 ? z1 >= size[1] : z1 <= -size[1])) keep_min(x, x1);
+  }
   return x;
 }
 
-B2_HD double ray_ellipsoid(const GeomPose& P, const double size[3], const double pnt[3],
-                           const double vec[3]) {
-  double lpnt[3], lvec[3];
-  ray_map(P, pnt, vec, lpnt, lvec);
+B2_HD double local_ellipsoid(const double size[3], const double lpnt[3], const double lvec[3]) {
   const double s0 = 1 / (size[0] * size[0]), s1 = 1 / (size[1] * size[1]),
                s2 = 1 / (size[2] * size[2]);
   const double a = s0 * lvec[0] * lvec[0] + s1 * lvec[1] * lvec[1] + s2 * lvec[2] * lvec[2];
@@ -159,15 +299,10 @@ B2_HD double ray_ellipsoid(const GeomPose& P, const double size[3], const double
   return ray_quad(a, b, c, x0, x1);
 }
 
-B2_HD double ray_cylinder(const GeomPose& P, const double size[3], const double pnt[3],
-                          const double vec[3]) {
-  const double ssz = size[0] * size[0] + size[1] * size[1];
-  if (ray_sphere(P.pos, ssz, pnt, vec) < 0) return -1;
-  double lpnt[3], lvec[3];
-  ray_map(P, pnt, vec, lpnt, lvec);
+B2_HD double local_cylinder(const double size[3], const double lpnt[3], const double lvec[3]) {
   double x = -1;
   if (fabs(lvec[2]) > kMinVal) {
-#pragma unroll
+#pragma unroll 1
     for (int side = -1; side <= 1; side += 2) {
       const double sol = (side * size[1] - lpnt[2]) / lvec[2];
       if (sol >= 0) {
@@ -186,48 +321,77 @@ B2_HD double ray_cylinder(const GeomPose& P, const double size[3], const double 
   return x;
 }
 
-// one face pair of the box test: axis i, the other two axes j,k
-#define B2_BOX_AXIS(i, j, k)                                                        \
-  if (fabs(lvec[i]) > kMinVal) {                                                    \
-    _Pragma("unroll") for (int side = -1; side <= 1; side += 2) {                   \
-      const double sol = (side * size[i] - lpnt[i]) / lvec[i];                      \
-      if (sol >= 0) {                                                               \
-        const double p0 = lpnt[j] + sol * lvec[j];                                  \
-        const double p1 = lpnt[k] + sol * lvec[k];                                  \
-        if (fabs(p0) <= size[j] && fabs(p1) <= size[k]) keep_min(x, sol);           \
-      }                                                                             \
-    }                                                                               \
-  }
-
-B2_HD double ray_box(const GeomPose& P, const double size[3], const double pnt[3],
-                     const double vec[3]) {
-  const double ssz = size[0] * size[0] + size[1] * size[1] + size[2] * size[2];
-  if (ray_sphere(P.pos, ssz, pnt, vec) < 0) return -1;
-  double lpnt[3], lvec[3];
-  ray_map(P, pnt, vec, lpnt, lvec);
+// box faces: the axis loop is kept rolled by rotating (axis, other, other); the acceptance test is
+// symmetric in the two other axes and keep_min is order independent, so every accepted `sol` is
+// the same arithmetic as upstream's ifcs table.
+B2_HD double local_box(const double size[3], const double lpnt[3], const double lvec[3]) {
   double x = -1;
-  B2_BOX_AXIS(0, 1, 2)
-  B2_BOX_AXIS(1, 0, 2)
-  B2_BOX_AXIS(2, 0, 1)
+  double a0 = lpnt[0], a1 = lpnt[1], a2 = lpnt[2];
+  double b0 = lvec[0], b1 = lvec[1], b2 = lvec[2];
+  double s0 = size[0], s1 = size[1], s2 = size[2];
+#pragma unroll 1
+  for (int it = 0; it < 3; it++) {
+    if (fabs(b0) > kMinVal) {
+#pragma unroll 1
+      for (int side = -1; side <= 1; side += 2) {
+        const double sol = (side * s0 - a0) / b0;
+        if (sol >= 0) {
+          const double p0 = a1 + sol * b1;
+          const double p1 = a2 + sol * b2;
+          if (fabs(p0) <= s1 && fabs(p1) <= s2) keep_min(x, sol);
+        }
+      }
+    }
+    double t = a0;
+    a0 = a1;
+    a1 = a2;
+    a2 = t;
+    t = b0;
+    b0 = b1;
+    b1 = b2;
+    b2 = t;
+    t = s0;
+    s0 = s1;
+    s1 = s2;
+    s2 = t;
+  }
   return x;
 }
 
-// mju_rayGeom for the primitive types (mesh handled by mesh_trace)
-B2_HD double ray_geom(int type, const GeomPose& P, const double size[3], const double pnt[3],
-                      const double vec[3]) {
+// mju_rayGeom for one primitive geom (also the geom_size box of a mesh geom when type = GEOM_BOX
+// is forced by the caller).  Out of line on the device: one copy serves every call site.
+B2_LEAF double prim_test(int type, const GeomPose* gp, const GeomStatic* gsp, double px, double py,
+                         double pz, double vx, double vy, double vz) {
+  const GeomPose P = ld_pose(gp);
+  const GeomStatic gs = ld_gstat(gsp);
+  const double pnt[3] = {px, py, pz}, vec[3] = {vx, vy, vz};
+  if (type == GEOM_SPHERE) return ray_sphere(P.pos, gs.size[0] * gs.size[0], pnt, vec);
+  // bounding-sphere pre-tests of capsule / cylinder / box
+  if (type == GEOM_CAPSULE || type == GEOM_CYLINDER || type == GEOM_BOX) {
+    double ssz;
+    if (type == GEOM_CAPSULE) {
+      const double s = gs.size[0] + gs.size[1];
+      ssz = s * s;
+    } else if (type == GEOM_CYLINDER) {
+      ssz = gs.size[0] * gs.size[0] + gs.size[1] * gs.size[1];
+    } else {
+      ssz = gs.size[0] * gs.size[0] + gs.size[1] * gs.size[1] + gs.size[2] * gs.size[2];
+    }
+    if (ray_sphere(P.pos, ssz, pnt, vec) < 0) return -1;
+  }
+  double lpnt[3], lvec[3];
+  ray_map(P, pnt, vec, lpnt, lvec);
   switch (type) {
     case GEOM_PLANE:
-      return ray_plane(P, size, pnt, vec);
-    case GEOM_SPHERE:
-      return ray_sphere(P.pos, size[0] * size[0], pnt, vec);
+      return local_plane(gs.size, lpnt, lvec);
     case GEOM_CAPSULE:
-      return ray_capsule(P, size, pnt, vec);
+      return local_capsule(gs.size, lpnt, lvec);
     case GEOM_ELLIPSOID:
-      return ray_ellipsoid(P, size, pnt, vec);
+      return local_ellipsoid(gs.size, lpnt, lvec);
     case GEOM_CYLINDER:
-      return ray_cylinder(P, size, pnt, vec);
+      return local_cylinder(gs.size, lpnt, lvec);
     case GEOM_BOX:
-      return ray_box(P, size, pnt, vec);
+      return local_box(gs.size, lpnt, lvec);
     default:
       return -1;
   }
@@ -303,20 +467,24 @@ B2_HD double ray_triangle(const float* fv0, const float* fv1, const float* fv2,
 }
 
 // ---------------------------------------------------------------------------------------------
-// conservative fp32 image of an fp64 ray, for slab culling
+// conservative fp32 image of an fp64 ray for slab culling, in FMA form:
+//   t_near_k = pn_k * an_k - bn_k     (never above the true entry parameter)
+//   t_far_k  = pf_k * af_k - bf_k     (never below the true exit parameter)
+// an/af are 1/v shrunk/grown by 8 ulp (covers the float casts, the reciprocal and the final
+// rounding of the fma), bn/bf are (origin +- 2 ulp) * an/af with directed rounding, so the only
+// cancellation (pn*an against bn) happens inside one exactly-rounded fma.
 // ---------------------------------------------------------------------------------------------
 struct RayF {
-  float on[3], of[3];  // origin to use with the near / far plane of each axis
-  float in[3], ifr[3]; // 1/v shrunk (near) and grown (far) by the accumulated rounding bound
+  float an[3], bn[3], af[3], bf[3];
   bool neg[3];
 };
 
 B2_HD void rayf_setup(RayF& r, const double o[3], const double v[3]) {
-  const float kEps = 4.76837158e-07f;  // 8 * 2^-24: covers sub, rcp, cast, mul and scale roundings
+  const float kEps = 4.76837158e-07f;  // 8 * 2^-24
 #pragma unroll
   for (int k = 0; k < 3; k++) {
     const float of = (float)o[k];
-    const float eo = fabsf(of) * 2.4e-7f + 1e-37f;  // >= 2 ulp: |o - of| <= 0.5 ulp
+    const float eo = fabsf(of) * 2.4e-7f + 1e-37f;  // >= 2 ulp, while |o - of| <= 0.5 ulp
     const float ohi = of + eo, olo = of - eo;
     const float vf = (float)v[k];
     const bool ng = v[k] < 0;
@@ -324,10 +492,11 @@ B2_HD void rayf_setup(RayF& r, const double o[3], const double v[3]) {
     float inv = 1.0f / av;
     if (ng) inv = -inv;
     r.neg[k] = ng;
-    r.in[k] = inv * (1.0f - kEps);
-    r.ifr[k] = inv * (1.0f + kEps);
-    r.on[k] = ng ? olo : ohi;
-    r.of[k] = ng ? ohi : olo;
+    r.an[k] = inv * (1.0f - kEps);
+    r.af[k] = inv * (1.0f + kEps);
+    // near plane uses the origin pushed along the ray, far plane the origin pulled back
+    r.bn[k] = fmul_up(ng ? olo : ohi, r.an[k]);
+    r.bf[k] = fmul_down(ng ? ohi : olo, r.af[k]);
   }
 }
 
@@ -339,8 +508,8 @@ B2_HD bool slab_test(const RayF& r, const float lo[3], const float hi[3], float 
   for (int k = 0; k < 3; k++) {
     const float pn = r.neg[k] ? hi[k] : lo[k];
     const float pf = r.neg[k] ? lo[k] : hi[k];
-    tn = fmaxf(tn, (pn - r.on[k]) * r.in[k]);
-    tf = fminf(tf, (pf - r.of[k]) * r.ifr[k]);
+    tn = fmaxf(tn, fma_rn(pn, r.an[k], -r.bn[k]));
+    tf = fminf(tf, fma_rn(pf, r.af[k], -r.bf[k]));
   }
   tnear = tn;
   return tn <= tf;
@@ -402,19 +571,21 @@ B2_HD float hit_tmax(const Hit& h, float tcap) {
 
 // ---------------------------------------------------------------------------------------------
 // per-lane traversal of one mesh BVH (mj_rayMesh).  No warp-level operations: lanes call this
-// for different meshes at the same time.
+// for different meshes at the same time.  Out of line on the device.
 // ---------------------------------------------------------------------------------------------
-template <class Ld>
-B2_HD double mesh_trace(const CastParams& p, int g, const GeomStatic& gs, const GeomPose& P,
-                        const double pnt[3], const double vec[3], float tcap, const Ld& ld) {
+B2_LEAF double mesh_trace(const MeshInfo* mesh, const BvhNode* mnodes, const MeshTri* mtris,
+                          const GeomPose* gp, const GeomStatic* gsp, double px, double py,
+                          double pz, double vx, double vy, double vz, float tcap) {
+  const GeomPose P = ld_pose(gp);
+  const double pnt[3] = {px, py, pz}, vec[3] = {vx, vy, vz};
   double lpnt[3], lvec[3], b0[3], b1[3];
   ray_map(P, pnt, vec, lpnt, lvec);
   mesh_ray_basis(lvec, b0, b1);
   RayF rf;
   rayf_setup(rf, lpnt, lvec);
-  const MeshInfo mi = p.mesh[gs.dataid];
-  const BvhNode* nodes = p.mnodes + mi.node_base;
-  const MeshTri* tris = p.mtris + mi.tri_base;
+  const MeshInfo mi = mesh[gsp->dataid];
+  const BvhNode* nodes = mnodes + mi.node_base;
+  const MeshTri* tris = mtris + mi.tri_base;
 
   double x = -1;
   float tmax = tcap;
@@ -422,19 +593,20 @@ B2_HD double mesh_trace(const CastParams& p, int g, const GeomStatic& gs, const 
   int sp = 0;
   int32_t cur = 0;
   while (true) {
-    const BvhNode n = ld.node(nodes + cur);
+    const BvhNode n = ld_node(nodes + cur);
     float t0, t1;
     bool h0 = slab_test(rf, n.lo0, n.hi0, tmax, t0);
     bool h1 = slab_test(rf, n.lo1, n.hi1, tmax, t1);
-#pragma unroll
+#pragma unroll 1
     for (int c = 0; c < 2; c++) {
       const bool h = c ? h1 : h0;
       const int32_t link = c ? n.c1 : n.c0;
       if (h && link < 0) {
         const int32_t payload = ~link;
         const int first = payload >> 2, cnt = (payload & 3) + 1;
+#pragma unroll 1
         for (int i = 0; i < cnt; i++) {
-          const MeshTri tr = ld.tri(tris + first + i);
+          const MeshTri tr = ld_tri(tris + first + i);
           const double sol = ray_triangle(tr.v0, tr.v1, tr.v2, lpnt, lvec, b0, b1);
           if (sol >= 0 && (x < 0 || sol < x)) {
             x = sol;
@@ -459,113 +631,310 @@ B2_HD double mesh_trace(const CastParams& p, int g, const GeomStatic& gs, const 
     }
   }
   // mj_rayMesh's box pre-test on geom_size, applied after the fact (same result, paid on hits only)
-  if (x >= 0 && ray_box(P, gs.size, pnt, vec) < 0) x = -1;
+  if (x >= 0 && prim_test(GEOM_BOX, gp, gsp, px, py, pz, vx, vy, vz) < 0) x = -1;
   return x;
 }
 
+// per-lane list of mesh geoms whose box the ray enters; traced after the primitives
+struct MeshCands {
+  float t[kMaxMeshCand];
+  int32_t g[kMaxMeshCand];
+  int n;
+};
+
+B2_HD void mesh_defer(const CastParams& p, const GeomPose* pose, MeshCands& mc, Hit& hit, int g,
+                      float tnear, const double pnt[3], const double vec[3], float tcap) {
+  if (mc.n < kMaxMeshCand) {
+    mc.t[mc.n] = tnear;
+    mc.g[mc.n] = g;
+    mc.n++;
+  } else {  // list full: resolve this one now
+    hit_update(hit,
+               mesh_trace(p.mesh, p.mnodes, p.mtris, pose + g, p.gstat + g, pnt[0], pnt[1], pnt[2],
+                          vec[0], vec[1], vec[2], hit_tmax(hit, tcap)),
+               g);
+  }
+}
+
+B2_HD void mesh_resolve(const CastParams& p, const GeomPose* pose, MeshCands& mc, Hit& hit,
+                        const double pnt[3], const double vec[3], float tcap) {
+  while (mc.n > 0) {  // nearest box first
+    int best = 0;
+    for (int i = 1; i < mc.n; i++)
+      if (mc.t[i] < mc.t[best]) best = i;
+    const float t = mc.t[best];
+    const int g = mc.g[best];
+    mc.n--;
+    mc.t[best] = mc.t[mc.n];
+    mc.g[best] = mc.g[mc.n];
+    const float tmax = hit_tmax(hit, tcap);
+    if (t > tmax) continue;
+    hit_update(hit,
+               mesh_trace(p.mesh, p.mnodes, p.mtris, pose + g, p.gstat + g, pnt[0], pnt[1], pnt[2],
+                          vec[0], vec[1], vec[2], tmax),
+               g);
+  }
+}
+
+// one geom leaf some lane's ray may touch (warp-uniform g); h = this lane's slab test passed
+B2_HD void leaf_visit(const CastParams& p, const GeomPose* pose, int g, bool h, float tnear,
+                      MeshCands& mc, Hit& hit, const double pnt[3], const double vec[3],
+                      float tcap) {
+  const int type = ld_geom_type(p.gstat + g);
+  if (!h) return;
+  if (type == GEOM_MESH) {
+    mesh_defer(p, pose, mc, hit, g, tnear, pnt, vec, tcap);
+  } else {
+    hit_update(hit,
+               prim_test(type, pose + g, p.gstat + g, pnt[0], pnt[1], pnt[2], vec[0], vec[1],
+                         vec[2]),
+               g);
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
-// one ray of a warp packet.  W supplies the warp votes and the per-warp stack; every lane of the
-// warp must call trace_ray together (lanes without a ray pass active = false).
+// fallback: per-node packet traversal with a shared stack (tiles whose rays are too incoherent for
+// the collect phase).  Every lane of the warp must take part.
 // ---------------------------------------------------------------------------------------------
-template <class W, class Ld>
-B2_HD Hit trace_ray(const CastParams& p, const BvhNode* tlas, const GeomPose* pose, bool active,
-                    const double pnt[3], const double vec[3], float tcap, W& warp, const Ld& ld) {
+template <bool STAGE, class W>
+B2_HD void trace_packet(const CastParams& p, const BvhNode* tlas, const GeomPose* pose, bool active,
+                        const double pnt[3], const double vec[3], float tcap, const RayF& rf,
+                        MeshCands& mc, Hit& hit, W& warp) {
+  int sp = 0;
+  int32_t cur = 0;
+  while (true) {
+    const BvhNode n = ld_tlas<STAGE>(tlas + cur);
+    const float tmax = hit_tmax(hit, tcap);
+    float t0 = 0.f, t1 = 0.f;
+    const bool h0 = active && slab_test(rf, n.lo0, n.hi0, tmax, t0);
+    const bool h1 = active && slab_test(rf, n.lo1, n.hi1, tmax, t1);
+    unsigned m0 = warp.ballot(h0), m1 = warp.ballot(h1);
+#pragma unroll 1
+    for (int c = 0; c < 2; c++) {
+      const int32_t link = c ? n.c1 : n.c0;
+      const unsigned m = c ? m1 : m0;
+      if (m != 0u && link < 0) {  // warp-uniform: a geom leaf some lane touches
+        const int g = ~link;
+        if (!ld_u8(p.elim + g)) leaf_visit(p, pose, g, c ? h1 : h0, c ? t1 : t0, mc, hit, pnt, vec, tcap);
+      }
+    }
+    if (n.c0 < 0) m0 = 0u;
+    if (n.c1 < 0) m1 = 0u;
+    if (m0 != 0u && m1 != 0u) {
+      // both inner children wanted: descend into the one most lanes enter first
+      const unsigned near0 = warp.ballot(h0 && (!h1 || t0 <= t1));
+      const unsigned near1 = warp.ballot(h1 && (!h0 || t1 < t0));
+      const bool first0 = warp.popc(near0) >= warp.popc(near1);
+      warp.push(sp, first0 ? n.c1 : n.c0);
+      cur = first0 ? n.c0 : n.c1;
+    } else if (m0 != 0u) {
+      cur = n.c0;
+    } else if (m1 != 0u) {
+      cur = n.c1;
+    } else {
+      if (sp == 0) break;
+      cur = warp.pop(sp);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// tile cone vs box (conservative).  The cone (apex o, unit axis a, half-angle theta) contains
+// every ray of the tile; a box is kept if its bounding sphere may touch the cone.
+// ---------------------------------------------------------------------------------------------
+struct TileCone {
+  float o[3], a[3];
+  float cos_t, sin_t;
+  float omag;   // |ox|+|oy|+|oz| for the rounding slack
+  float far;    // farthest distance (world units) any lane still needs
+  bool wide;    // half-angle too large for the test: keep everything
+};
+
+B2_HD bool cone_box(const TileCone& tc, const float lo[3], const float hi[3], float& key) {
+  // distance from the apex to the box (ordering key, conservative lower bound)
+  float d2 = 0.f, cx[3], r2 = 0.f;
+#pragma unroll
+  for (int k = 0; k < 3; k++) {
+    const float d = fmaxf(fmaxf(lo[k] - tc.o[k], tc.o[k] - hi[k]), 0.f);
+    d2 += d * d;
+    cx[k] = 0.5f * (lo[k] + hi[k]) - tc.o[k];
+    const float h = 0.5f * (hi[k] - lo[k]);
+    r2 += h * h;
+  }
+  const float d = sqrtf(d2);
+  key = fmaxf(0.f, d * (1.0f - 1e-5f) - 1e-6f * (tc.omag + d));
+  if (key > tc.far) return false;
+  if (tc.wide) return true;
+  const float r = sqrtf(r2);
+  const float c2 = cx[0] * cx[0] + cx[1] * cx[1] + cx[2] * cx[2];
+  const float along = cx[0] * tc.a[0] + cx[1] * tc.a[1] + cx[2] * tc.a[2];
+  const float perp = sqrtf(fmaxf(c2 - along * along, 0.f));
+  const float slack = r * 1e-4f + 1e-5f * (sqrtf(c2) + tc.omag) + 1e-6f;
+  // signed distance from the sphere centre to the cone's lateral surface
+  const float ds = perp * tc.cos_t - along * tc.sin_t;
+  if (ds > r + slack) return false;
+  // behind the apex the nearest feature is the apex itself
+  const float e = along * tc.cos_t + perp * tc.sin_t;
+  if (e < 0.f && c2 > (r + slack) * (r + slack)) return false;
+  return true;
+}
+
+// ---------------------------------------------------------------------------------------------
+// one ray of a warp tile.  Every lane of the warp must call trace_tile together (lanes without a
+// ray pass active = false); all rays of the tile share the origin pnt.
+// ---------------------------------------------------------------------------------------------
+template <bool STAGE, class W>
+B2_HD Hit trace_tile(const CastParams& p, const BvhNode* tlas, const GeomPose* pose, bool active,
+                     const double pnt[3], const double vec[3], float tcap, W& warp) {
   Hit hit;
   hit.dist = -1;
   hit.id = -1;
 
-  // planes live outside the BVH (unbounded)
+  // 1. planes live outside the BVH (unbounded); their hit bounds everything that follows
   for (int i = 0; i < p.nplane; i++) {
     const int g = p.plane_ids[i];
-    if (p.elim[g]) continue;
-    if (active) {
-      const GeomPose P = ld.pose(pose + g);
-      const GeomStatic gs = ld.gstat(p.gstat + g);
-      hit_update(hit, ray_geom(GEOM_PLANE, P, gs.size, pnt, vec), g);
-    }
+    if (ld_u8(p.elim + g)) continue;
+    if (active)
+      hit_update(hit,
+                 prim_test(GEOM_PLANE, pose + g, p.gstat + g, pnt[0], pnt[1], pnt[2], vec[0],
+                           vec[1], vec[2]),
+                 g);
   }
+  if (p.nnode == 0 || !warp.any(active)) return hit;
 
   RayF rf;
   rayf_setup(rf, pnt, vec);
+  MeshCands mc;
+  mc.n = 0;
 
-  // deferred mesh candidates of this lane
-  float cand_t[kMaxMeshCand];
-  int32_t cand_g[kMaxMeshCand];
-  int ncand = 0;
-
-  if (p.nnode > 0) {
-    int sp = 0;
-    int32_t cur = 0;
-    while (true) {
-      const BvhNode n = ld.tlas_node(tlas + cur);
-      const float tmax = hit_tmax(hit, tcap);
-      float t0, t1;
-      const bool h0 = active && slab_test(rf, n.lo0, n.hi0, tmax, t0);
-      const bool h1 = active && slab_test(rf, n.lo1, n.hi1, tmax, t1);
-      unsigned m0 = warp.ballot(h0), m1 = warp.ballot(h1);
+  // 2. tile cone: axis = mean unit direction, half-angle = largest deviation (+ slack)
+  TileCone tc;
+  float df[3] = {0.f, 0.f, 0.f};
+  float vlen_up = 0.f;
+  if (active) {
+    const double vlen = sqrt(dot3(vec, vec));
+    const double inv = 1.0 / vlen;
+    df[0] = (float)(vec[0] * inv);
+    df[1] = (float)(vec[1] * inv);
+    df[2] = (float)(vec[2] * inv);
+    vlen_up = f32_up(vlen) * (1.0f + 1e-6f);
+  }
+  const float ax = warp.sum(df[0]), ay = warp.sum(df[1]), az = warp.sum(df[2]);
+  const float an = sqrtf(ax * ax + ay * ay + az * az);
+  tc.wide = !(an > 1e-3f);
+  const float ian = tc.wide ? 0.f : 1.0f / an;
+  tc.a[0] = ax * ian;
+  tc.a[1] = ay * ian;
+  tc.a[2] = az * ian;
+  const float cmin = warp.min(active ? df[0] * tc.a[0] + df[1] * tc.a[1] + df[2] * tc.a[2] : 1.0f);
+  tc.cos_t = fminf(fmaxf(cmin - 4e-6f, -1.0f), 1.0f);
+  if (tc.cos_t < 0.2f) tc.wide = true;
+  tc.sin_t = sqrtf(fmaxf(1.0f - tc.cos_t * tc.cos_t, 0.f)) + 4e-6f;
+  tc.omag = 0.f;
 #pragma unroll
-      for (int c = 0; c < 2; c++) {
-        const int32_t link = c ? n.c1 : n.c0;
-        const unsigned m = c ? m1 : m0;
-        if (m != 0u && link < 0) {  // warp-uniform: a geom leaf some lane touches
-          const int g = ~link;
-          if (!p.elim[g]) {
-            const GeomStatic gs = ld.gstat(p.gstat + g);
-            const bool h = c ? h1 : h0;
-            if (h) {
-              if (gs.type == GEOM_MESH) {
-                if (ncand < kMaxMeshCand) {
-                  cand_t[ncand] = c ? t1 : t0;
-                  cand_g[ncand] = g;
-                  ncand++;
-                } else {  // candidate list full: resolve this one now
-                  const GeomPose P = ld.pose(pose + g);
-                  hit_update(hit, mesh_trace(p, g, gs, P, pnt, vec, hit_tmax(hit, tcap), ld), g);
-                }
-              } else {
-                const GeomPose P = ld.pose(pose + g);
-                hit_update(hit, ray_geom(gs.type, P, gs.size, pnt, vec), g);
-              }
-            }
-          }
+  for (int k = 0; k < 3; k++) {
+    tc.o[k] = (float)pnt[k];
+    tc.omag += fabsf(tc.o[k]);
+  }
+  // farthest world distance any lane still has to search
+  tc.far = warp.max(active ? hit_tmax(hit, tcap) * vlen_up : 0.f);
+
+  // 3. COLLECT: breadth-ish walk, up to one node per lane per round
+  int32_t* queue = warp.queue();
+  F4* cand_a = warp.cand_a();  // lo.xyz, key
+  F4* cand_b = warp.cand_b();  // hi.xyz, geom id bits
+  const int L = warp.size();
+  int nq = 1, nc = 0;
+  bool overflow = false;
+  if (warp.lane() == 0) queue[0] = 0;
+  warp.sync();
+  while (nq > 0) {
+    const int take = nq < L ? nq : L;
+    const int base = nq - take;
+    const int my = warp.lane() < take ? queue[base + warp.lane()] : -1;
+    warp.sync();  // the slots just read may be overwritten below
+    nq = base;
+    BvhNode n;
+    bool pass0 = false, pass1 = false;
+    float key0 = 0.f, key1 = 0.f;
+    if (my >= 0) {
+      n = ld_tlas<STAGE>(tlas + my);
+      pass0 = n.c0 != kEmptyChild && cone_box(tc, n.lo0, n.hi0, key0);
+      pass1 = n.c1 != kEmptyChild && cone_box(tc, n.lo1, n.hi1, key1);
+    }
+#pragma unroll
+    for (int c = 0; c < 2; c++) {
+      const bool pass = c ? pass1 : pass0;
+      const int32_t link = (my >= 0) ? (c ? n.c1 : n.c0) : 0;
+      const bool inner = pass && link >= 0;
+      const bool leaf = pass && link < 0 && !ld_u8(p.elim + (~link));
+      const unsigned mi = warp.ballot(inner), ml = warp.ballot(leaf);
+      if (inner) {
+        const int pos = nq + warp.popc(mi & warp.lanemask_lt());
+        if (pos < kQueueCap) queue[pos] = link;
+      }
+      if (leaf) {
+        const int pos = nc + warp.popc(ml & warp.lanemask_lt());
+        if (pos < kCandCap) {
+          const float* lo = c ? n.lo1 : n.lo0;
+          const float* hi = c ? n.hi1 : n.hi0;
+          F4 a, b;
+          a.x = lo[0];
+          a.y = lo[1];
+          a.z = lo[2];
+          a.w = c ? key1 : key0;
+          b.x = hi[0];
+          b.y = hi[1];
+          b.z = hi[2];
+          b.w = int_as_f32(~link);
+          cand_a[pos] = a;
+          cand_b[pos] = b;
         }
       }
-      if (n.c0 < 0) m0 = 0u;
-      if (n.c1 < 0) m1 = 0u;
-      if (m0 != 0u && m1 != 0u) {
-        // both inner children wanted: descend into the one most lanes enter first
-        const unsigned near0 = warp.ballot(h0 && (!h1 || t0 <= t1));
-        const unsigned near1 = warp.ballot(h1 && (!h0 || t1 < t0));
-        const bool first0 = warp.popc(near0) >= warp.popc(near1);
-        warp.push(sp, first0 ? n.c1 : n.c0);
-        cur = first0 ? n.c0 : n.c1;
-      } else if (m0 != 0u) {
-        cur = n.c0;
-      } else if (m1 != 0u) {
-        cur = n.c1;
-      } else {
-        if (sp == 0) break;
-        cur = warp.pop(sp);
+      nq += warp.popc(mi);
+      nc += warp.popc(ml);
+    }
+    if (nq > kQueueCap || nc > kCandCap) {
+      overflow = true;
+      break;
+    }
+    warp.sync();
+  }
+  warp.sync();
+
+  if (overflow) {
+    // 5. too many candidates / too wide a frontier: per-node packet traversal instead
+    trace_packet<STAGE>(p, tlas, pose, active, pnt, vec, tcap, rf, mc, hit, warp);
+  } else {
+    // rank sort by key (ties by slot): order[rank] = slot
+    int32_t* order = warp.order();
+    for (int i = warp.lane(); i < nc; i += L) {
+      const float ki = cand_a[i].w;
+      int rank = 0;
+      for (int j = 0; j < nc; j++) {
+        const float kj = cand_a[j].w;
+        rank += (kj < ki || (kj == ki && j < i)) ? 1 : 0;
       }
+      order[rank] = i;
+    }
+    warp.sync();
+    // 4. candidates, nearest first; all lanes test the same geom at the same time
+    for (int i = 0; i < nc; i++) {
+      const int slot = order[i];
+      const F4 a = cand_a[slot], b = cand_b[slot];
+      const float tmax = hit_tmax(hit, tcap);
+      const bool need = active && a.w <= tmax * vlen_up;
+      if (!warp.any(need)) break;  // sorted: nobody can improve on a later candidate either
+      const float lo[3] = {a.x, a.y, a.z}, hi[3] = {b.x, b.y, b.z};
+      float tn = 0.f;
+      const bool h = need && slab_test(rf, lo, hi, tmax, tn);
+      if (!warp.any(h)) continue;
+      leaf_visit(p, pose, f32_as_int(b.w), h, tn, mc, hit, pnt, vec, tcap);
     }
   }
 
   // deferred meshes, nearest box first, each lane on its own
-  while (ncand > 0) {
-    int best = 0;
-    for (int i = 1; i < ncand; i++)
-      if (cand_t[i] < cand_t[best]) best = i;
-    const float t = cand_t[best];
-    const int g = cand_g[best];
-    ncand--;
-    cand_t[best] = cand_t[ncand];
-    cand_g[best] = cand_g[ncand];
-    const float tmax = hit_tmax(hit, tcap);
-    if (t > tmax) continue;
-    const GeomStatic gs = ld.gstat(p.gstat + g);
-    const GeomPose P = ld.pose(pose + g);
-    hit_update(hit, mesh_trace(p, g, gs, P, pnt, vec, tmax, ld), g);
-  }
+  mesh_resolve(p, pose, mc, hit, pnt, vec, tcap);
   return hit;
 }
 
@@ -573,7 +942,7 @@ B2_HD Hit trace_ray(const CastParams& p, const BvhNode* tlas, const GeomPose* po
 // ray generation and the fused epilogues of the three cast modes (shared by the kernel and the
 // CPU emulation harness)
 // ---------------------------------------------------------------------------------------------
-// o / R: the scan's sensor frame.  Returns false for a degenerate (zero-length) ray.
+// R: the scan's sensor frame.  Returns false for a degenerate (zero-length) ray.
 B2_HD bool cast_make_ray(const CastParams& p, int mode, const double R[9], int r, double l[3],
                          double vec[3]) {
   if (mode == MODE_CAMERA) {

@@ -21,21 +21,26 @@ using namespace b2;
 namespace {
 
 struct HostWarp {
-  int32_t stack[kPacketStack];
+  F4 cand_a_[kCandCap], cand_b_[kCandCap];
+  int32_t queue_[kQueueCap], order_[kCandCap], stack[kPacketStack];
+  int size() const { return 1; }
+  int lane() const { return 0; }
+  unsigned lanemask_lt() const { return 0u; }
   unsigned ballot(bool p) const { return p ? 1u : 0u; }
+  bool any(bool p) const { return p; }
   int popc(unsigned m) const { return __builtin_popcount(m); }
+  void sync() const {}
+  float sum(float v) const { return v; }
+  float min(float v) const { return v; }
+  float max(float v) const { return v; }
+  int32_t* queue() { return queue_; }
+  F4* cand_a() { return cand_a_; }
+  F4* cand_b() { return cand_b_; }
+  int32_t* order() { return order_; }
   void push(int& sp, int32_t v) {
     if (sp < kPacketStack) stack[sp++] = v;
   }
   int32_t pop(int& sp) { return stack[--sp]; }
-};
-
-struct HostLd {
-  BvhNode node(const BvhNode* p) const { return *p; }
-  BvhNode tlas_node(const BvhNode* p) const { return *p; }
-  MeshTri tri(const MeshTri* p) const { return *p; }
-  GeomPose pose(const GeomPose* p) const { return *p; }
-  GeomStatic gstat(const GeomStatic* p) const { return *p; }
 };
 
 struct EmuScene {
@@ -138,12 +143,11 @@ void fill_params(const EmuScene& S, CastParams& p) {
 
 void run(const EmuScene& S, CastParams& p, const double o[3], const double* R) {
   HostWarp warp;
-  HostLd ld;
   const float tcap = p.mode == MODE_MULTIRAY ? f32_up(p.cutoff) : FLT_MAX;
   for (int r = 0; r < p.nray; r++) {
     double l[3], vec[3];
     const bool active = cast_make_ray(p, p.mode, R, r, l, vec);
-    const Hit hit = trace_ray(p, p.tlas, p.pose, active, o, vec, tcap, warp, ld);
+    const Hit hit = trace_tile<false>(p, p.tlas, p.pose, active, o, vec, tcap, warp);
     cast_epilogue(p, p.mode, 0, r, hit, l);
   }
 }

@@ -8,8 +8,8 @@ mkdir -p $OUT
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > $OUT/smi_$TAG.txt 2>&1
 python -m pytest tests -m gpu -x -q > $OUT/pytest_gpu_$TAG.log 2>&1; echo "pytest rc=$?" | tee -a $OUT/pytest_gpu_$TAG.log
 python -c "import __graft_entry__ as g; g.smoke()" > $OUT/smoke_$TAG.log 2>&1; echo "smoke rc=$?" | tee -a $OUT/smoke_$TAG.log
-python bench.py > $OUT/bench_$TAG.json 2> $OUT/bench_$TAG.err; echo "bench rc=$?"; tail -c 3000 $OUT/bench_$TAG.json
-python bench.py --impl reference --steps 3 --warmup 1 > $OUT/bench_ref_$TAG.json 2> $OUT/bench_ref_$TAG.err; echo "bench ref rc=$?"
+python bench.py $BENCH_ARGS > $OUT/bench_$TAG.json 2> $OUT/bench_$TAG.err; echo "bench rc=$?"; tail -c 3000 $OUT/bench_$TAG.json
+if [ "${REF:-1}" = "1" ]; then python bench.py --impl reference --steps 3 --warmup 1 > $OUT/bench_ref_$TAG.json 2> $OUT/bench_ref_$TAG.err; echo "bench ref rc=$?"; fi
 if [ "${NCU:-1}" = "1" ]; then
   BCMD="python bench.py --steps 2 --warmup 3 --scans 256 --e2e-scans 32 --no-cpu-baseline"
   $BCMD > $OUT/plain_$TAG.log 2>&1 && \
@@ -18,7 +18,6 @@ if [ "${NCU:-1}" = "1" ]; then
   $BCMD > $OUT/plain2_$TAG.log 2>&1 && \
   ncu --set full --clock-control none --import-source on -k regex:cast_kernel -s 3 -c 1 -o $OUT/cast_$TAG $BCMD > $OUT/ncu_full_$TAG.log 2>&1
   echo "ncu full rc=$?"
-  ncu --set full --clock-control none --import-source on -k regex:depth_to_cloud -s 3 -c 1 -o $OUT/depth_$TAG $BCMD > $OUT/ncu_depth_$TAG.log 2>&1
-  echo "ncu depth rc=$?"
+  if [ "${NCU_DEPTH:-1}" = "1" ]; then ncu --set full --clock-control none --import-source on -k regex:depth_to_cloud -s 3 -c 1 -o $OUT/depth_$TAG $BCMD > $OUT/ncu_depth_$TAG.log 2>&1; echo "ncu depth rc=$?"; fi
 fi
 ls -la $OUT | tail -20
