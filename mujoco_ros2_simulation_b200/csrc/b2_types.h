@@ -48,6 +48,23 @@ struct B2_ALIGN(16) BvhNode {
 };
 static_assert(sizeof(BvhNode) == 64, "BvhNode must be 64 B");
 
+// The geom BVH is a wide tree (fanout <= 32) so that one warp tests all children of a node at
+// once, one lane per child.  A child slot holds the child's box and its link
+// (>= 0: wide node id, < 0: ~geom id).  Slots of one node are contiguous.
+constexpr int kWideFanout = 32;
+struct B2_ALIGN(16) WideChild {
+  float lo[3];
+  int32_t link;
+  float hi[3];
+  int32_t pad;
+};
+static_assert(sizeof(WideChild) == 32, "WideChild must be 32 B");
+
+struct WideNode {
+  int32_t first;  // first child slot
+  int32_t count;  // number of child slots (1..32)
+};
+
 struct B2_ALIGN(16) GeomStatic {
   double size[3];
   int32_t type;
@@ -83,14 +100,15 @@ enum CastMode : int32_t {
 // Everything one cast launch reads.  Passed by value as a __grid_constant__ kernel parameter.
 struct CastParams {
   // scene mirror
-  const BvhNode* tlas;      // [nworld][nnode]
+  const WideChild* wslots;  // [nworld][nslot] geom BVH child slots (boxes refit per step)
+  const WideNode* wnodes;   // [nwnode] geom BVH topology (node 0 = root)
   const GeomPose* pose;     // [nworld][ngeom]
   const GeomStatic* gstat;  // [ngeom]
   const int32_t* plane_ids; // [nplane] geoms kept outside the BVH
   const MeshInfo* mesh;     // [nmesh]
   const BvhNode* mnodes;
   const MeshTri* mtris;
-  int32_t nnode, ngeom, nplane, nworld;
+  int32_t nslot, nwnode, ngeom, nplane, nworld;
   // sensor
   const uint8_t* elim;      // [ngeom] ray_eliminate flags for this sensor
   const double* local_dir;  // [nray*3] (lidar table or multiray vec)

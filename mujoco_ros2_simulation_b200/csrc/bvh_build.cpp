@@ -232,3 +232,102 @@ BuiltBvh build_bvh(const std::vector<Aabb>& prims, int max_leaf, bool leaf_paylo
 }
 
 }  // namespace b2
+
+// ---------------------------------------------------------------------------------------------
+// BVH2 -> fanout-32 collapse (geom BVH).  A wide node starts as the two children of a BVH2 node and
+// repeatedly replaces its largest-area inner child by that child's two children until it holds 32
+// children or only geoms are left.
+// ---------------------------------------------------------------------------------------------
+namespace b2 {
+namespace {
+
+struct WItem {
+  int32_t link;  // BVH2 link: >= 0 inner node, < 0 leaf payload (~geom)
+  float area;
+};
+
+float child_area(const BvhNode& n, int which) {
+  const float* lo = which == 0 ? n.lo0 : n.lo1;
+  const float* hi = which == 0 ? n.hi0 : n.hi1;
+  const float dx = hi[0] - lo[0], dy = hi[1] - lo[1], dz = hi[2] - lo[2];
+  if (dx < 0 || dy < 0 || dz < 0) return 0.f;
+  return 2.f * (dx * dy + dy * dz + dz * dx);
+}
+
+}  // namespace
+
+WideBvh collapse_wide(const BuiltBvh& bvh2) {
+  WideBvh out;
+  if (bvh2.nodes.empty()) return out;
+  struct Pending {
+    int32_t bvh2_node;
+    int32_t wide_id;
+    int depth;
+  };
+  std::vector<Pending> todo;
+  out.nodes.push_back(WideNode{0, 0});
+  todo.push_back({0, 0, 1});
+  std::vector<int32_t> node_of_slot;
+  while (!todo.empty()) {
+    const Pending cur = todo.back();
+    todo.pop_back();
+    out.depth = std::max(out.depth, cur.depth);
+    std::vector<WItem> items;
+    auto add_children = [&](int32_t b2n) {
+      const BvhNode& n = bvh2.nodes[(size_t)b2n];
+      if (n.c0 != kEmptyChild) items.push_back({n.c0, child_area(n, 0)});
+      if (n.c1 != kEmptyChild) items.push_back({n.c1, child_area(n, 1)});
+    };
+    add_children(cur.bvh2_node);
+    while ((int)items.size() < kWideFanout) {
+      int best = -1;
+      for (int i = 0; i < (int)items.size(); i++)
+        if (items[i].link >= 0 && (best < 0 || items[i].area > items[best].area)) best = i;
+      if (best < 0) break;
+      const int32_t b2n = items[best].link;
+      items.erase(items.begin() + best);
+      add_children(b2n);
+    }
+    // geoms first, in id order (keeps coincident duplicates adjacent), then inner children
+    std::stable_sort(items.begin(), items.end(), [](const WItem& a, const WItem& b) {
+      const bool la = a.link < 0, lb = b.link < 0;
+      if (la != lb) return la;
+      if (la) return (~a.link) < (~b.link);
+      return false;
+    });
+    WideNode& wn = out.nodes[(size_t)cur.wide_id];
+    wn.first = (int32_t)out.slot_link.size();
+    wn.count = (int32_t)items.size();
+    for (const WItem& it : items) {
+      if (it.link < 0) {
+        out.slot_link.push_back(it.link);
+      } else {
+        const int32_t wid = (int32_t)out.nodes.size();
+        out.nodes.push_back(WideNode{0, 0});
+        out.slot_link.push_back(wid);
+        todo.push_back({it.link, wid, cur.depth + 1});
+      }
+      node_of_slot.push_back(cur.wide_id);
+    }
+  }
+  // heights: children always have a larger id than their parent
+  const int nn = (int)out.nodes.size();
+  std::vector<int> height(nn, 0);
+  for (int i = nn - 1; i >= 0; i--) {
+    int h = 0;
+    for (int s = out.nodes[i].first; s < out.nodes[i].first + out.nodes[i].count; s++)
+      if (out.slot_link[s] >= 0) h = std::max(h, height[out.slot_link[s]] + 1);
+    height[i] = h;
+  }
+  const int nlevel = *std::max_element(height.begin(), height.end()) + 1;
+  const int nslot = (int)out.slot_link.size();
+  out.refit_level_start.assign(nlevel + 1, 0);
+  for (int s = 0; s < nslot; s++) out.refit_level_start[height[node_of_slot[s]] + 1]++;
+  for (int l = 0; l < nlevel; l++) out.refit_level_start[l + 1] += out.refit_level_start[l];
+  out.refit_slots.resize(nslot);
+  std::vector<int> cursor(out.refit_level_start.begin(), out.refit_level_start.end() - 1);
+  for (int s = 0; s < nslot; s++) out.refit_slots[cursor[height[node_of_slot[s]]]++] = s;
+  return out;
+}
+
+}  // namespace b2

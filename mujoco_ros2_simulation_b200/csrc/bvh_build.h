@@ -23,6 +23,18 @@ struct BuiltBvh {
   int max_depth = 0;
 };
 
+// Fanout-32 tree collapsed from a BVH2 whose leaves carry geom ids (the geom BVH).
+struct WideBvh {
+  std::vector<WideNode> nodes;       // node 0 = root
+  std::vector<int32_t> slot_link;    // [nslot] >= 0: wide node id, < 0: ~geom id
+  // refit schedule: slots sorted by the height of the node that owns them (height 0 first:
+  // a slot of height h only depends on nodes of height < h)
+  std::vector<int32_t> refit_slots;
+  std::vector<int32_t> refit_level_start;  // [nlevel+1]
+  int depth = 0;                           // nodes on the longest root-to-leaf path
+};
+WideBvh collapse_wide(const BuiltBvh& bvh2);
+
 // prims: one box per primitive.  max_leaf: primitives per leaf (1 for geoms, <=4 for triangles).
 // leaf_payload_geom: true  -> leaf payload = primitive id (max_leaf must be 1)
 //                    false -> leaf payload = (first << 2) | (count - 1) into `order`

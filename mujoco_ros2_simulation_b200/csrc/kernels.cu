@@ -21,6 +21,9 @@ constexpr size_t kStageLimit = 96 * 1024;  // largest geom BVH staged in shared 
 int cast_tiles_per_scan(int nray) { return (nray + 31) / 32; }
 int cast_threads_per_block() { return kCastThreads; }
 size_t cast_stage_limit_bytes() { return kStageLimit; }
+size_t cast_stage_bytes(int nslot, int nwnode) {
+  return (size_t)nslot * sizeof(WideChild) + (size_t)nwnode * sizeof(WideNode);
+}
 
 // =============================================================================================
 // K1: refit
@@ -29,7 +32,7 @@ __global__ void __launch_bounds__(128) refit_kernel(const RefitParams p) {
   const int w_local = blockIdx.x;
   const int world = p.world0 + w_local;
   GeomPose* pose = p.pose + (size_t)world * p.ngeom;
-  BvhNode* tlas = p.tlas + (size_t)world * p.nnode;
+  WideChild* slots = p.wslots + (size_t)world * p.nslot;
 
   // 1. pack mjData geom_xpos / geom_xmat into 16-B aligned GeomPose records
   if (p.raw_xpos != nullptr) {
@@ -44,34 +47,34 @@ __global__ void __launch_bounds__(128) refit_kernel(const RefitParams p) {
     __syncthreads();
   }
 
-  // 2. bottom-up: level 0 nodes have only geom leaves, level l nodes only children below l
+  // 2. bottom-up over child slots: a slot of level l is a geom (box from its pose) or an inner
+  //    node whose own slots all belong to levels < l (written by this CTA in an earlier pass)
   for (int l = 0; l < p.nlevel; l++) {
     const int beg = p.level_start[l], end = p.level_start[l + 1];
     for (int i = beg + threadIdx.x; i < end; i += blockDim.x) {
-      const int node = p.refit_nodes[i];
-      BvhNode n = p.topo[node];
-#pragma unroll
-      for (int c = 0; c < 2; c++) {
-        const int32_t link = c ? n.c1 : n.c0;
-        float* lo = c ? n.lo1 : n.lo0;
-        float* hi = c ? n.hi1 : n.hi0;
-        if (link == kEmptyChild) {
-          lo[0] = lo[1] = lo[2] = FLT_MAX;
-          hi[0] = hi[1] = hi[2] = -FLT_MAX;
-        } else if (link < 0) {
-          const int g = ~link;
-          const GeomStatic gs = p.gstat[g];
-          geom_aabb(gs.type, gs.size, pose[g], lo, hi);
-        } else {
-          const BvhNode ch = tlas[link];  // written by this CTA at a lower level
+      const int s = p.refit_slots[i];
+      const int32_t link = p.slot_link[s];
+      WideChild out;
+      out.link = link;
+      out.pad = 0;
+      if (link < 0) {
+        const int g = ~link;
+        const GeomStatic gs = p.gstat[g];
+        geom_aabb(gs.type, gs.size, pose[g], out.lo, out.hi);
+      } else {
+        const WideNode wn = p.wnodes[link];
+        out.lo[0] = out.lo[1] = out.lo[2] = FLT_MAX;
+        out.hi[0] = out.hi[1] = out.hi[2] = -FLT_MAX;
+        for (int c = wn.first; c < wn.first + wn.count; c++) {
+          const WideChild ch = slots[c];
 #pragma unroll
           for (int k = 0; k < 3; k++) {
-            lo[k] = fminf(ch.lo0[k], ch.lo1[k]);
-            hi[k] = fmaxf(ch.hi0[k], ch.hi1[k]);
+            out.lo[k] = fminf(out.lo[k], ch.lo[k]);
+            out.hi[k] = fmaxf(out.hi[k], ch.hi[k]);
           }
         }
       }
-      tlas[node] = n;
+      slots[s] = out;
     }
     __syncthreads();
   }
@@ -94,7 +97,6 @@ struct WarpScratch {
   F4 cand_b[kCandCap];          // candidate box hi.xyz + geom id bits
   int32_t queue[kQueueCap];     // collect frontier
   int32_t order[kCandCap];      // rank-sorted candidate slots
-  int32_t stack[kPacketStack];  // fallback packet traversal
 };
 
 struct DevWarp {
@@ -128,17 +130,6 @@ struct DevWarp {
   __device__ __forceinline__ F4* cand_a() const { return s->cand_a; }
   __device__ __forceinline__ F4* cand_b() const { return s->cand_b; }
   __device__ __forceinline__ int32_t* order() const { return s->order; }
-  __device__ __forceinline__ void push(int& sp, int32_t v) {
-    if (sp < kPacketStack) {
-      if (lane_ == 0) s->stack[sp] = v;
-      sp++;
-    }
-    __syncwarp();
-  }
-  __device__ __forceinline__ int32_t pop(int& sp) {
-    --sp;
-    return s->stack[sp];
-  }
 };
 
 // ray index of (tile, lane): 8x4 tiles over (scan line, line index) for 3-D sensors, else 32x1
@@ -156,31 +147,28 @@ __global__ void __launch_bounds__(kCastThreads)
                 const int tiles_per_scan, const int chunks_per_scan, const int tiles_x) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   WarpScratch* scratch = reinterpret_cast<WarpScratch*>(smem_raw);
-  BvhNode* s_tlas = reinterpret_cast<BvhNode*>(smem_raw + kCastWarps * sizeof(WarpScratch));
+  unsigned char* s_stage = smem_raw + kCastWarps * sizeof(WarpScratch);
 
   const int warp_id = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int scan = blockIdx.x / chunks_per_scan;
   const int chunk = blockIdx.x - scan * chunks_per_scan;
   const int world = p.scan_world ? p.scan_world[scan] : scan % p.nworld;
 
-  const BvhNode* tlas = p.tlas + (size_t)world * p.nnode;
+  // geom BVH of this world: child slots (boxes) + topology, staged in shared memory per CTA
+  const WideChild* wslots = p.wslots + (size_t)world * p.nslot;
+  const WideNode* wnodes = p.wnodes;
   if (STAGE) {
-    const float4* src = reinterpret_cast<const float4*>(tlas);
-    float4* dst = reinterpret_cast<float4*>(s_tlas);
-    for (int i = threadIdx.x; i < p.nnode * 4; i += kCastThreads) dst[i] = __ldg(src + i);
+    const float4* src = reinterpret_cast<const float4*>(wslots);
+    float4* dst = reinterpret_cast<float4*>(s_stage);
+    for (int i = threadIdx.x; i < p.nslot * 2; i += kCastThreads) dst[i] = __ldg(src + i);
+    int2* ndst = reinterpret_cast<int2*>(s_stage + (size_t)p.nslot * sizeof(WideChild));
+    const int2* nsrc = reinterpret_cast<const int2*>(p.wnodes);
+    for (int i = threadIdx.x; i < p.nwnode; i += kCastThreads) ndst[i] = __ldg(nsrc + i);
     __syncthreads();
-    tlas = s_tlas;
+    wslots = reinterpret_cast<const WideChild*>(s_stage);
+    wnodes = reinterpret_cast<const WideNode*>(ndst);
   }
   const GeomPose* pose = p.pose + (size_t)world * p.ngeom;
-
-  // sensor frame (warp-uniform)
-  double o[3], R[9];
-#pragma unroll
-  for (int k = 0; k < 3; k++) o[k] = __ldg(p.spos + (size_t)scan * 3 + k);
-  if (MODE != MODE_MULTIRAY) {
-#pragma unroll
-    for (int k = 0; k < 9; k++) R[k] = __ldg(p.smat + (size_t)scan * 9 + k);
-  }
 
   DevWarp warp{scratch + warp_id, lane};
   const float tcap = (MODE == MODE_MULTIRAY) ? f32_up(p.cutoff) : FLT_MAX;
@@ -192,12 +180,27 @@ __global__ void __launch_bounds__(kCastThreads)
     bool active = r < p.nray;
     const int rr = active ? r : 0;
 
-    double l[3], vec[3];
+    // sensor frame (warp-uniform, L1-resident): reloaded per tile so it is not live across the
+    // traversal
+    double o[3], R[9], l[3], vec[3];
+#pragma unroll
+    for (int k = 0; k < 3; k++) o[k] = __ldg(p.spos + (size_t)scan * 3 + k);
+    if (MODE != MODE_MULTIRAY) {
+#pragma unroll
+      for (int k = 0; k < 9; k++) R[k] = __ldg(p.smat + (size_t)scan * 9 + k);
+    }
     active = cast_make_ray(p, MODE, R, rr, l, vec) && active;
 
-    const Hit hit = trace_tile<STAGE>(p, tlas, pose, active, o, vec, tcap, warp);
+    const Hit hit = trace_tile<STAGE>(p, wslots, wnodes, pose, active, o, vec, tcap, warp);
 
-    if (r < p.nray) cast_epilogue(p, MODE, scan, r, hit, l);
+    if (r < p.nray) {
+      double le[3] = {0.0, 0.0, 0.0};
+      if (MODE == MODE_LIDAR && p.xyz != nullptr) {  // reloaded, not kept live across the trace
+#pragma unroll
+        for (int k = 0; k < 3; k++) le[k] = __ldg(p.local_dir + (size_t)r * 3 + k);
+      }
+      cast_epilogue(p, MODE, scan, r, hit, le);
+    }
   }
 }
 
@@ -220,7 +223,7 @@ static cudaError_t launch_cast_mode(const CastParams& p, bool stage, int tiles_p
   if (nblocks <= 0) return cudaSuccess;
   if (nblocks > 0x7fffffffLL) return cudaErrorInvalidConfiguration;
   size_t smem = kCastWarps * sizeof(WarpScratch);
-  if (stage) smem += (size_t)p.nnode * sizeof(BvhNode);
+  if (stage) smem += cast_stage_bytes(p.nslot, p.nwnode);
   cudaError_t err;
   if (stage) {
     auto k = cast_kernel<MODE, true>;
@@ -238,7 +241,7 @@ static cudaError_t launch_cast_mode(const CastParams& p, bool stage, int tiles_p
 
 cudaError_t launch_cast(const CastParams& p, bool stage_tlas, int tiles_per_block,
                         cudaStream_t stream) {
-  if (p.nnode == 0 || (size_t)p.nnode * sizeof(BvhNode) > kStageLimit) stage_tlas = false;
+  if (p.nwnode == 0 || cast_stage_bytes(p.nslot, p.nwnode) > kStageLimit) stage_tlas = false;
   switch (p.mode) {
     case MODE_LIDAR:
       return launch_cast_mode<MODE_LIDAR>(p, stage_tlas, tiles_per_block, stream);

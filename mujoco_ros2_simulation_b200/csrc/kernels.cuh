@@ -14,12 +14,13 @@ struct RefitParams {
   const double* raw_xmat;  // [nworld][ngeom][9]
   // ... written to / read from the packed scene mirror of worlds [world0, world0+nworld)
   GeomPose* pose;           // [nworld_total][ngeom]
-  BvhNode* tlas;            // [nworld_total][nnode]
+  WideChild* wslots;        // [nworld_total][nslot] child slots of the wide geom BVH
   const GeomStatic* gstat;  // [ngeom]
-  const BvhNode* topo;      // [nnode] child links of the shared topology
-  const int32_t* refit_nodes;  // [nnode] nodes sorted by height
+  const WideNode* wnodes;   // [nwnode] shared topology
+  const int32_t* slot_link; // [nslot] >= 0: wide node id, < 0: ~geom id
+  const int32_t* refit_slots;  // [nslot] slots sorted by the height of their node
   const int32_t* level_start;  // [nlevel+1]
-  int32_t ngeom, nnode, nlevel, world0, nworld;
+  int32_t ngeom, nslot, nlevel, world0, nworld;
 };
 
 struct DepthParams {
@@ -42,6 +43,7 @@ cudaError_t launch_cast(const CastParams& p, bool stage_tlas, int tiles_per_bloc
 int cast_tiles_per_scan(int nray);
 int cast_threads_per_block();
 size_t cast_stage_limit_bytes();
+size_t cast_stage_bytes(int nslot, int nwnode);  // shared memory the staged geom BVH needs
 
 // K3: depth linearise + flip + PointCloud2 projection.
 cudaError_t launch_depth_to_cloud(const DepthParams& p, cudaStream_t stream);

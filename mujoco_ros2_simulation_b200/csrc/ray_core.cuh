@@ -12,17 +12,7 @@
 // conservative culling (tile cone vs box, slab tests against outward-rounded boxes) and can never
 // drop a hit the double test would accept.
 //
-// Traversal (one warp = one tile of 32 rays that share an origin):
-//   1. planes (kept outside the BVH) are tested first: they bound the search distance;
-//   2. COLLECT: the warp walks the geom BVH once for the whole tile -- each lane tests a different
-//      node's two child boxes against the tile's bounding cone and against the farthest distance
-//      any lane still needs -- and gathers the surviving geoms into a shared-memory candidate list;
-//   3. candidates are rank-sorted by their distance from the origin and visited in that order by
-//      all lanes together: per-lane conservative slab test, then the closed-form fp64 test of the
-//      (warp-uniform) geom type; the loop ends as soon as no lane can still improve;
-//   4. mesh geoms a lane's ray enters are deferred and traced per lane through the mesh BVH;
-//   5. tiles whose candidate set does not fit (incoherent rays) fall back to a per-node packet
-//      traversal with a shared stack.
+// The warp-cooperative traversal itself lives in tile_trace.cuh (included at the end).
 #ifndef B2_RAY_CORE_CUH
 #define B2_RAY_CORE_CUH
 
@@ -47,11 +37,10 @@ namespace b2 {
 #define B2_LEAF static inline
 #endif
 
-constexpr int kPacketStack = 64;  // geom-BVH stack entries per warp (fallback traversal)
 constexpr int kMeshStack = 64;    // mesh-BVH stack entries per lane
 constexpr int kMaxMeshCand = 12;  // deferred mesh candidates per lane
-constexpr int kQueueCap = 96;     // collect frontier (node ids) per warp
-constexpr int kCandCap = 64;      // candidate geoms per tile
+constexpr int kQueueCap = 160;    // collect frontier (wide node ids) per warp: 1 + 31 * depth
+constexpr int kCandCap = 96;      // candidate geoms per tile between two drains
 
 struct B2_ALIGN(16) F4 {
   float x, y, z, w;
@@ -136,22 +125,31 @@ B2_HD BvhNode ld_node(const BvhNode* ptr) {
   return *ptr;
 #endif
 }
-// geom-BVH node: shared memory when staged (generic load), else the read-only path
+// one child slot of the wide geom BVH: shared memory when staged, else the read-only path
 template <bool STAGE>
-B2_HD BvhNode ld_tlas(const BvhNode* ptr) {
+B2_HD WideChild ld_wslot(const WideChild* ptr) {
 #if B2_ON_DEVICE
+  WideChild c;
+  const float4* q = reinterpret_cast<const float4*>(ptr);
+  float4* o = reinterpret_cast<float4*>(&c);
   if (STAGE) {
-    BvhNode n;
-    const float4* q = reinterpret_cast<const float4*>(ptr);
-    float4* o = reinterpret_cast<float4*>(&n);
     o[0] = q[0];
     o[1] = q[1];
-    o[2] = q[2];
-    o[3] = q[3];
-    return n;
+  } else {
+    o[0] = __ldg(q);
+    o[1] = __ldg(q + 1);
   }
+  return c;
+#else
+  return *ptr;
 #endif
-  return ld_node(ptr);
+}
+B2_HD float rsqrt_f32(float x) {
+#if B2_ON_DEVICE
+  return rsqrtf(x);
+#else
+  return 1.0f / sqrtf(x);
+#endif
 }
 B2_HD MeshTri ld_tri(const MeshTri* ptr) {
 #if B2_ON_DEVICE
@@ -693,252 +691,6 @@ B2_HD void leaf_visit(const CastParams& p, const GeomPose* pose, int g, bool h, 
 }
 
 // ---------------------------------------------------------------------------------------------
-// fallback: per-node packet traversal with a shared stack (tiles whose rays are too incoherent for
-// the collect phase).  Every lane of the warp must take part.
-// ---------------------------------------------------------------------------------------------
-template <bool STAGE, class W>
-B2_HD void trace_packet(const CastParams& p, const BvhNode* tlas, const GeomPose* pose, bool active,
-                        const double pnt[3], const double vec[3], float tcap, const RayF& rf,
-                        MeshCands& mc, Hit& hit, W& warp) {
-  int sp = 0;
-  int32_t cur = 0;
-  while (true) {
-    const BvhNode n = ld_tlas<STAGE>(tlas + cur);
-    const float tmax = hit_tmax(hit, tcap);
-    float t0 = 0.f, t1 = 0.f;
-    const bool h0 = active && slab_test(rf, n.lo0, n.hi0, tmax, t0);
-    const bool h1 = active && slab_test(rf, n.lo1, n.hi1, tmax, t1);
-    unsigned m0 = warp.ballot(h0), m1 = warp.ballot(h1);
-#pragma unroll 1
-    for (int c = 0; c < 2; c++) {
-      const int32_t link = c ? n.c1 : n.c0;
-      const unsigned m = c ? m1 : m0;
-      if (m != 0u && link < 0) {  // warp-uniform: a geom leaf some lane touches
-        const int g = ~link;
-        if (!ld_u8(p.elim + g)) leaf_visit(p, pose, g, c ? h1 : h0, c ? t1 : t0, mc, hit, pnt, vec, tcap);
-      }
-    }
-    if (n.c0 < 0) m0 = 0u;
-    if (n.c1 < 0) m1 = 0u;
-    if (m0 != 0u && m1 != 0u) {
-      // both inner children wanted: descend into the one most lanes enter first
-      const unsigned near0 = warp.ballot(h0 && (!h1 || t0 <= t1));
-      const unsigned near1 = warp.ballot(h1 && (!h0 || t1 < t0));
-      const bool first0 = warp.popc(near0) >= warp.popc(near1);
-      warp.push(sp, first0 ? n.c1 : n.c0);
-      cur = first0 ? n.c0 : n.c1;
-    } else if (m0 != 0u) {
-      cur = n.c0;
-    } else if (m1 != 0u) {
-      cur = n.c1;
-    } else {
-      if (sp == 0) break;
-      cur = warp.pop(sp);
-    }
-  }
-}
-
-// ---------------------------------------------------------------------------------------------
-// tile cone vs box (conservative).  The cone (apex o, unit axis a, half-angle theta) contains
-// every ray of the tile; a box is kept if its bounding sphere may touch the cone.
-// ---------------------------------------------------------------------------------------------
-struct TileCone {
-  float o[3], a[3];
-  float cos_t, sin_t;
-  float omag;   // |ox|+|oy|+|oz| for the rounding slack
-  float far;    // farthest distance (world units) any lane still needs
-  bool wide;    // half-angle too large for the test: keep everything
-};
-
-B2_HD bool cone_box(const TileCone& tc, const float lo[3], const float hi[3], float& key) {
-  // distance from the apex to the box (ordering key, conservative lower bound)
-  float d2 = 0.f, cx[3], r2 = 0.f;
-#pragma unroll
-  for (int k = 0; k < 3; k++) {
-    const float d = fmaxf(fmaxf(lo[k] - tc.o[k], tc.o[k] - hi[k]), 0.f);
-    d2 += d * d;
-    cx[k] = 0.5f * (lo[k] + hi[k]) - tc.o[k];
-    const float h = 0.5f * (hi[k] - lo[k]);
-    r2 += h * h;
-  }
-  const float d = sqrtf(d2);
-  key = fmaxf(0.f, d * (1.0f - 1e-5f) - 1e-6f * (tc.omag + d));
-  if (key > tc.far) return false;
-  if (tc.wide) return true;
-  const float r = sqrtf(r2);
-  const float c2 = cx[0] * cx[0] + cx[1] * cx[1] + cx[2] * cx[2];
-  const float along = cx[0] * tc.a[0] + cx[1] * tc.a[1] + cx[2] * tc.a[2];
-  const float perp = sqrtf(fmaxf(c2 - along * along, 0.f));
-  const float slack = r * 1e-4f + 1e-5f * (sqrtf(c2) + tc.omag) + 1e-6f;
-  // signed distance from the sphere centre to the cone's lateral surface
-  const float ds = perp * tc.cos_t - along * tc.sin_t;
-  if (ds > r + slack) return false;
-  // behind the apex the nearest feature is the apex itself
-  const float e = along * tc.cos_t + perp * tc.sin_t;
-  if (e < 0.f && c2 > (r + slack) * (r + slack)) return false;
-  return true;
-}
-
-// ---------------------------------------------------------------------------------------------
-// one ray of a warp tile.  Every lane of the warp must call trace_tile together (lanes without a
-// ray pass active = false); all rays of the tile share the origin pnt.
-// ---------------------------------------------------------------------------------------------
-template <bool STAGE, class W>
-B2_HD Hit trace_tile(const CastParams& p, const BvhNode* tlas, const GeomPose* pose, bool active,
-                     const double pnt[3], const double vec[3], float tcap, W& warp) {
-  Hit hit;
-  hit.dist = -1;
-  hit.id = -1;
-
-  // 1. planes live outside the BVH (unbounded); their hit bounds everything that follows
-  for (int i = 0; i < p.nplane; i++) {
-    const int g = p.plane_ids[i];
-    if (ld_u8(p.elim + g)) continue;
-    if (active)
-      hit_update(hit,
-                 prim_test(GEOM_PLANE, pose + g, p.gstat + g, pnt[0], pnt[1], pnt[2], vec[0],
-                           vec[1], vec[2]),
-                 g);
-  }
-  if (p.nnode == 0 || !warp.any(active)) return hit;
-
-  RayF rf;
-  rayf_setup(rf, pnt, vec);
-  MeshCands mc;
-  mc.n = 0;
-
-  // 2. tile cone: axis = mean unit direction, half-angle = largest deviation (+ slack)
-  TileCone tc;
-  float df[3] = {0.f, 0.f, 0.f};
-  float vlen_up = 0.f;
-  if (active) {
-    const double vlen = sqrt(dot3(vec, vec));
-    const double inv = 1.0 / vlen;
-    df[0] = (float)(vec[0] * inv);
-    df[1] = (float)(vec[1] * inv);
-    df[2] = (float)(vec[2] * inv);
-    vlen_up = f32_up(vlen) * (1.0f + 1e-6f);
-  }
-  const float ax = warp.sum(df[0]), ay = warp.sum(df[1]), az = warp.sum(df[2]);
-  const float an = sqrtf(ax * ax + ay * ay + az * az);
-  tc.wide = !(an > 1e-3f);
-  const float ian = tc.wide ? 0.f : 1.0f / an;
-  tc.a[0] = ax * ian;
-  tc.a[1] = ay * ian;
-  tc.a[2] = az * ian;
-  const float cmin = warp.min(active ? df[0] * tc.a[0] + df[1] * tc.a[1] + df[2] * tc.a[2] : 1.0f);
-  tc.cos_t = fminf(fmaxf(cmin - 4e-6f, -1.0f), 1.0f);
-  if (tc.cos_t < 0.2f) tc.wide = true;
-  tc.sin_t = sqrtf(fmaxf(1.0f - tc.cos_t * tc.cos_t, 0.f)) + 4e-6f;
-  tc.omag = 0.f;
-#pragma unroll
-  for (int k = 0; k < 3; k++) {
-    tc.o[k] = (float)pnt[k];
-    tc.omag += fabsf(tc.o[k]);
-  }
-  // farthest world distance any lane still has to search
-  tc.far = warp.max(active ? hit_tmax(hit, tcap) * vlen_up : 0.f);
-
-  // 3. COLLECT: breadth-ish walk, up to one node per lane per round
-  int32_t* queue = warp.queue();
-  F4* cand_a = warp.cand_a();  // lo.xyz, key
-  F4* cand_b = warp.cand_b();  // hi.xyz, geom id bits
-  const int L = warp.size();
-  int nq = 1, nc = 0;
-  bool overflow = false;
-  if (warp.lane() == 0) queue[0] = 0;
-  warp.sync();
-  while (nq > 0) {
-    const int take = nq < L ? nq : L;
-    const int base = nq - take;
-    const int my = warp.lane() < take ? queue[base + warp.lane()] : -1;
-    warp.sync();  // the slots just read may be overwritten below
-    nq = base;
-    BvhNode n;
-    bool pass0 = false, pass1 = false;
-    float key0 = 0.f, key1 = 0.f;
-    if (my >= 0) {
-      n = ld_tlas<STAGE>(tlas + my);
-      pass0 = n.c0 != kEmptyChild && cone_box(tc, n.lo0, n.hi0, key0);
-      pass1 = n.c1 != kEmptyChild && cone_box(tc, n.lo1, n.hi1, key1);
-    }
-#pragma unroll
-    for (int c = 0; c < 2; c++) {
-      const bool pass = c ? pass1 : pass0;
-      const int32_t link = (my >= 0) ? (c ? n.c1 : n.c0) : 0;
-      const bool inner = pass && link >= 0;
-      const bool leaf = pass && link < 0 && !ld_u8(p.elim + (~link));
-      const unsigned mi = warp.ballot(inner), ml = warp.ballot(leaf);
-      if (inner) {
-        const int pos = nq + warp.popc(mi & warp.lanemask_lt());
-        if (pos < kQueueCap) queue[pos] = link;
-      }
-      if (leaf) {
-        const int pos = nc + warp.popc(ml & warp.lanemask_lt());
-        if (pos < kCandCap) {
-          const float* lo = c ? n.lo1 : n.lo0;
-          const float* hi = c ? n.hi1 : n.hi0;
-          F4 a, b;
-          a.x = lo[0];
-          a.y = lo[1];
-          a.z = lo[2];
-          a.w = c ? key1 : key0;
-          b.x = hi[0];
-          b.y = hi[1];
-          b.z = hi[2];
-          b.w = int_as_f32(~link);
-          cand_a[pos] = a;
-          cand_b[pos] = b;
-        }
-      }
-      nq += warp.popc(mi);
-      nc += warp.popc(ml);
-    }
-    if (nq > kQueueCap || nc > kCandCap) {
-      overflow = true;
-      break;
-    }
-    warp.sync();
-  }
-  warp.sync();
-
-  if (overflow) {
-    // 5. too many candidates / too wide a frontier: per-node packet traversal instead
-    trace_packet<STAGE>(p, tlas, pose, active, pnt, vec, tcap, rf, mc, hit, warp);
-  } else {
-    // rank sort by key (ties by slot): order[rank] = slot
-    int32_t* order = warp.order();
-    for (int i = warp.lane(); i < nc; i += L) {
-      const float ki = cand_a[i].w;
-      int rank = 0;
-      for (int j = 0; j < nc; j++) {
-        const float kj = cand_a[j].w;
-        rank += (kj < ki || (kj == ki && j < i)) ? 1 : 0;
-      }
-      order[rank] = i;
-    }
-    warp.sync();
-    // 4. candidates, nearest first; all lanes test the same geom at the same time
-    for (int i = 0; i < nc; i++) {
-      const int slot = order[i];
-      const F4 a = cand_a[slot], b = cand_b[slot];
-      const float tmax = hit_tmax(hit, tcap);
-      const bool need = active && a.w <= tmax * vlen_up;
-      if (!warp.any(need)) break;  // sorted: nobody can improve on a later candidate either
-      const float lo[3] = {a.x, a.y, a.z}, hi[3] = {b.x, b.y, b.z};
-      float tn = 0.f;
-      const bool h = need && slab_test(rf, lo, hi, tmax, tn);
-      if (!warp.any(h)) continue;
-      leaf_visit(p, pose, f32_as_int(b.w), h, tn, mc, hit, pnt, vec, tcap);
-    }
-  }
-
-  // deferred meshes, nearest box first, each lane on its own
-  mesh_resolve(p, pose, mc, hit, pnt, vec, tcap);
-  return hit;
-}
-
-// ---------------------------------------------------------------------------------------------
 // ray generation and the fused epilogues of the three cast modes (shared by the kernel and the
 // CPU emulation harness)
 // ---------------------------------------------------------------------------------------------
@@ -1022,4 +774,6 @@ B2_HD void cast_epilogue(const CastParams& p, int mode, int scan, int r, const H
 }
 
 }  // namespace b2
+#include "tile_trace.cuh"
+
 #endif

@@ -105,12 +105,12 @@ struct b2_scene {
   long long n_mesh_nodes = 0, n_mesh_tris = 0;
   // device: per world
   DevBuf<GeomPose> d_pose;
-  DevBuf<BvhNode> d_tlas;
-  // geom BVH topology
+  DevBuf<WideChild> d_wslots;  // [nworld][nslot]
+  // geom BVH topology (fanout-32 tree, shared by all worlds)
   bool topo_built = false;
-  int nnode = 0, nlevel = 0;
-  DevBuf<BvhNode> d_topo;
-  DevBuf<int32_t> d_refit_nodes, d_level_start;
+  int nslot = 0, nwnode = 0, nlevel = 0, wide_depth = 0;
+  DevBuf<WideNode> d_wnodes;
+  DevBuf<int32_t> d_slot_link, d_refit_slots, d_level_start;
   // pose staging (double-buffered pinned host memory + device raw arrays)
   PinBuf<double> h_stage[2];
   cudaEvent_t stage_done[2] = {nullptr, nullptr};
@@ -176,28 +176,33 @@ int build_meshes(b2_scene* s, const b2_model_desc* m) {
 
 // topology of the geom BVH from one world's poses (host arrays, [ngeom*3] / [ngeom*9])
 int build_topology(b2_scene* s, const double* xpos, const double* xmat) {
-  BuiltBvh bvh;
+  WideBvh w;
   std::string err;
-  if (!build_geom_topology(s->hm, xpos, xmat, kPacketStack - 2, bvh, err))
+  if (!build_geom_topology(s->hm, xpos, xmat, kMaxWideDepth, w, err))
     return fail(B2_ERR_UNSUPPORTED, err);
-  const int nnode = (int)bvh.nodes.size();
-  if (s->topo_built && nnode != s->nnode)
-    return fail(B2_ERR_INVALID, "internal: node count changed on rebuild");
-  s->nnode = nnode;
-  s->nlevel = (int)bvh.refit_level_start.size() - 1;
+  const int nslot = (int)w.slot_link.size(), nwnode = (int)w.nodes.size();
+  if (s->topo_built && nslot != s->nslot)
+    return fail(B2_ERR_INVALID, "internal: slot count changed on rebuild");
+  s->nslot = nslot;
+  s->nwnode = nwnode;
+  s->wide_depth = w.depth;
+  s->nlevel = (int)w.refit_level_start.size() - 1;
   if (s->nlevel < 0) s->nlevel = 0;
-  if (nnode > 0) {
-    B2_CUDA(s->d_topo.reserve((size_t)nnode));
-    B2_CUDA(cudaMemcpyAsync(s->d_topo.ptr, bvh.nodes.data(), (size_t)nnode * sizeof(BvhNode),
+  if (nslot > 0) {
+    B2_CUDA(s->d_wnodes.reserve((size_t)nwnode));
+    B2_CUDA(cudaMemcpyAsync(s->d_wnodes.ptr, w.nodes.data(), (size_t)nwnode * sizeof(WideNode),
                             cudaMemcpyHostToDevice, s->stream));
-    B2_CUDA(s->d_refit_nodes.reserve((size_t)nnode));
-    B2_CUDA(cudaMemcpyAsync(s->d_refit_nodes.ptr, bvh.refit_nodes.data(),
-                            (size_t)nnode * sizeof(int32_t), cudaMemcpyHostToDevice, s->stream));
+    B2_CUDA(s->d_slot_link.reserve((size_t)nslot));
+    B2_CUDA(cudaMemcpyAsync(s->d_slot_link.ptr, w.slot_link.data(), (size_t)nslot * sizeof(int32_t),
+                            cudaMemcpyHostToDevice, s->stream));
+    B2_CUDA(s->d_refit_slots.reserve((size_t)nslot));
+    B2_CUDA(cudaMemcpyAsync(s->d_refit_slots.ptr, w.refit_slots.data(),
+                            (size_t)nslot * sizeof(int32_t), cudaMemcpyHostToDevice, s->stream));
     B2_CUDA(s->d_level_start.reserve((size_t)s->nlevel + 1));
-    B2_CUDA(cudaMemcpyAsync(s->d_level_start.ptr, bvh.refit_level_start.data(),
+    B2_CUDA(cudaMemcpyAsync(s->d_level_start.ptr, w.refit_level_start.data(),
                             ((size_t)s->nlevel + 1) * sizeof(int32_t), cudaMemcpyHostToDevice,
                             s->stream));
-    B2_CUDA(s->d_tlas.reserve((size_t)nnode * s->nworld));
+    B2_CUDA(s->d_wslots.reserve((size_t)nslot * s->nworld));
     // the host vectors die at return: the copies above must have consumed them
     B2_CUDA(cudaStreamSynchronize(s->stream));
   }
@@ -210,13 +215,14 @@ int run_refit(b2_scene* s, int world0, int nworld, const double* d_xpos, const d
   rp.raw_xpos = d_xpos;
   rp.raw_xmat = d_xmat;
   rp.pose = s->d_pose.ptr;
-  rp.tlas = s->d_tlas.ptr;
+  rp.wslots = s->d_wslots.ptr;
   rp.gstat = s->d_gstat.ptr;
-  rp.topo = s->d_topo.ptr;
-  rp.refit_nodes = s->d_refit_nodes.ptr;
+  rp.wnodes = s->d_wnodes.ptr;
+  rp.slot_link = s->d_slot_link.ptr;
+  rp.refit_slots = s->d_refit_slots.ptr;
   rp.level_start = s->d_level_start.ptr;
   rp.ngeom = s->ngeom;
-  rp.nnode = s->nnode;
+  rp.nslot = s->nslot;
   rp.nlevel = s->nlevel;
   rp.world0 = world0;
   rp.nworld = nworld;
@@ -226,14 +232,16 @@ int run_refit(b2_scene* s, int world0, int nworld, const double* d_xpos, const d
 }
 
 void fill_cast_scene(const b2_scene* s, CastParams& p) {
-  p.tlas = s->d_tlas.ptr;
+  p.wslots = s->d_wslots.ptr;
+  p.wnodes = s->d_wnodes.ptr;
   p.pose = s->d_pose.ptr;
   p.gstat = s->d_gstat.ptr;
   p.plane_ids = s->d_plane_ids.ptr;
   p.mesh = s->d_mesh.ptr;
   p.mnodes = s->d_mnodes.ptr;
   p.mtris = s->d_mtris.ptr;
-  p.nnode = s->nnode;
+  p.nslot = s->nslot;
+  p.nwnode = s->nwnode;
   p.ngeom = s->ngeom;
   p.nplane = (int)s->hm.plane_ids.size();
   p.nworld = s->nworld;
@@ -250,7 +258,7 @@ void cast_shape(const b2_scene* s, const CastParams& p, bool& stage, int& tiles_
   if (tpb < warps) tpb = warps;
   if (tpb > 8 * warps) tpb = 8 * warps;
   tiles_per_block = env_int("B2_TILES_PER_BLOCK", (int)tpb);
-  const size_t bytes = (size_t)p.nnode * sizeof(BvhNode);
+  const size_t bytes = cast_stage_bytes(p.nslot, p.nwnode);
   stage = bytes > 0 && bytes <= cast_stage_limit_bytes() &&
           (tiles_per_block >= 4 * warps || bytes <= 4096);
   const int force = env_int("B2_STAGE", -1);
@@ -402,9 +410,10 @@ int b2_scene_destroy(b2_scene* s) {
   s->d_mnodes.release();
   s->d_mtris.release();
   s->d_pose.release();
-  s->d_tlas.release();
-  s->d_topo.release();
-  s->d_refit_nodes.release();
+  s->d_wslots.release();
+  s->d_wnodes.release();
+  s->d_slot_link.release();
+  s->d_refit_slots.release();
   s->d_level_start.release();
   s->d_raw.release();
   s->d_mr_vec.release();
@@ -510,7 +519,7 @@ int b2_scene_sync(b2_scene* s) {
 int b2_scene_stats(const b2_scene* s, int32_t* n_bvh_nodes, int32_t* n_planes,
                    int64_t* n_mesh_nodes, int64_t* n_mesh_tris) {
   if (!s) return fail(B2_ERR_INVALID, "null scene");
-  if (n_bvh_nodes) *n_bvh_nodes = s->nnode;
+  if (n_bvh_nodes) *n_bvh_nodes = s->nslot;
   if (n_planes) *n_planes = (int32_t)s->hm.plane_ids.size();
   if (n_mesh_nodes) *n_mesh_nodes = s->n_mesh_nodes;
   if (n_mesh_tris) *n_mesh_tris = s->n_mesh_tris;

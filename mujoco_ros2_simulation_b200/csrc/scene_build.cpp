@@ -105,7 +105,8 @@ bool build_mesh_bvhs(int nmesh, const int32_t* vertadr, const int32_t* vertnum,
 }
 
 bool build_geom_topology(const HostModel& m, const double* xpos, const double* xmat, int max_depth,
-                         BuiltBvh& out, std::string& err) {
+                         WideBvh& wide, std::string& err) {
+  BuiltBvh out;
   std::vector<Aabb> boxes;
   boxes.reserve(m.bvh_geoms.size());
   for (int g : m.bvh_geoms) {
@@ -117,14 +118,15 @@ bool build_geom_topology(const HostModel& m, const double* xpos, const double* x
     boxes.push_back(b);
   }
   out = build_bvh(boxes, 1, true, 4.0f);
-  if (out.max_depth > max_depth) {
-    err = "geom BVH deeper than the traversal stack";
-    return false;
-  }
   // leaf payloads index `boxes`; map them to geom ids
   for (auto& n : out.nodes) {
     if (n.c0 < 0 && n.c0 != kEmptyChild) n.c0 = ~m.bvh_geoms[(size_t)(~n.c0)];
     if (n.c1 < 0 && n.c1 != kEmptyChild) n.c1 = ~m.bvh_geoms[(size_t)(~n.c1)];
+  }
+  wide = collapse_wide(out);
+  if (wide.depth > max_depth) {
+    err = "geom BVH deeper than the traversal frontier allows";
+    return false;
   }
   return true;
 }

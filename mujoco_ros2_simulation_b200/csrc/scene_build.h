@@ -37,9 +37,10 @@ bool build_mesh_bvhs(int nmesh, const int32_t* vertadr, const int32_t* vertnum,
                      const int32_t* face, int max_leaf, int max_depth, HostMeshes& out,
                      std::string& err);
 
-// geom-BVH topology from one world's poses; leaf payloads are geom ids
+// geom-BVH topology from one world's poses: binned-SAH BVH2 collapsed to fanout 32; leaf links
+// are ~geom id.  max_depth: deepest wide tree the traversal's frontier queue can hold.
 bool build_geom_topology(const HostModel& m, const double* xpos, const double* xmat, int max_depth,
-                         BuiltBvh& out, std::string& err);
+                         WideBvh& out, std::string& err);
 
 }  // namespace b2
 #endif

@@ -1,10 +1,11 @@
 // emu.cpp -- CPU EMULATION HARNESS of the cast kernel's traversal logic.  TEST INFRASTRUCTURE ONLY.
 //
-// Compiles the product's __host__ __device__ traversal (csrc/ray_core.cuh: trace_ray, mesh_trace,
-// the fp64 leaf tests, the conservative fp32 slabs, geom_aabb) and its host-side scene
-// construction (csrc/scene_build.cpp, csrc/bvh_build.cpp) for the CPU, with a 1-lane "warp", so
-// the logic that runs on the B200 can be compared with the oracle in the CPU-only test tier.
-// It is never linked into libb2sense.so and is not a fallback: the product has no CPU path.
+// Compiles the product's __host__ __device__ traversal (csrc/ray_core.cuh + csrc/tile_trace.cuh:
+// trace_tile, mesh_trace, the fp64 leaf tests, the conservative fp32 slabs and cone test,
+// geom_aabb) and its host-side scene construction (csrc/scene_build.cpp, csrc/bvh_build.cpp) for
+// the CPU, with a 1-lane "warp", so the logic that runs on the B200 can be compared with the
+// oracle in the CPU-only test tier.  It is never linked into libb2sense.so and is not a fallback:
+// the product has no CPU path.
 #include <cmath>
 #include <cstring>
 #include <string>
@@ -22,7 +23,7 @@ namespace {
 
 struct HostWarp {
   F4 cand_a_[kCandCap], cand_b_[kCandCap];
-  int32_t queue_[kQueueCap], order_[kCandCap], stack[kPacketStack];
+  int32_t queue_[kQueueCap], order_[kCandCap];
   int size() const { return 1; }
   int lane() const { return 0; }
   unsigned lanemask_lt() const { return 0u; }
@@ -37,10 +38,6 @@ struct HostWarp {
   F4* cand_a() { return cand_a_; }
   F4* cand_b() { return cand_b_; }
   int32_t* order() { return order_; }
-  void push(int& sp, int32_t v) {
-    if (sp < kPacketStack) stack[sp++] = v;
-  }
-  int32_t pop(int& sp) { return stack[--sp]; }
 };
 
 struct EmuScene {
@@ -48,37 +45,37 @@ struct EmuScene {
   HostMeshes meshes;
   std::vector<GeomStatic> gstat;
   std::vector<GeomPose> pose;
-  BuiltBvh topo;
-  std::vector<BvhNode> tlas;
+  WideBvh topo;
+  std::vector<WideChild> slots;
 };
 
 // the refit kernel's per-world work, serially (kernels.cu refit_kernel)
 void host_refit(EmuScene& S) {
-  S.tlas = S.topo.nodes;
+  const int nslot = (int)S.topo.slot_link.size();
+  S.slots.assign((size_t)nslot, WideChild{});
   const int nlevel = (int)S.topo.refit_level_start.size() - 1;
   for (int l = 0; l < nlevel; l++) {
     for (int i = S.topo.refit_level_start[l]; i < S.topo.refit_level_start[l + 1]; i++) {
-      const int node = S.topo.refit_nodes[i];
-      BvhNode n = S.topo.nodes[node];
-      for (int c = 0; c < 2; c++) {
-        const int32_t link = c ? n.c1 : n.c0;
-        float* lo = c ? n.lo1 : n.lo0;
-        float* hi = c ? n.hi1 : n.hi0;
-        if (link == kEmptyChild) {
-          lo[0] = lo[1] = lo[2] = FLT_MAX;
-          hi[0] = hi[1] = hi[2] = -FLT_MAX;
-        } else if (link < 0) {
-          const int g = ~link;
-          geom_aabb(S.gstat[g].type, S.gstat[g].size, S.pose[g], lo, hi);
-        } else {
-          const BvhNode& ch = S.tlas[link];
-          for (int k = 0; k < 3; k++) {
-            lo[k] = fminf(ch.lo0[k], ch.lo1[k]);
-            hi[k] = fmaxf(ch.hi0[k], ch.hi1[k]);
-          }
+      const int s = S.topo.refit_slots[i];
+      const int32_t link = S.topo.slot_link[s];
+      WideChild out{};
+      out.link = link;
+      if (link < 0) {
+        const int g = ~link;
+        geom_aabb(S.gstat[g].type, S.gstat[g].size, S.pose[g], out.lo, out.hi);
+      } else {
+        const WideNode wn = S.topo.nodes[link];
+        for (int k = 0; k < 3; k++) {
+          out.lo[k] = FLT_MAX;
+          out.hi[k] = -FLT_MAX;
         }
+        for (int c = wn.first; c < wn.first + wn.count; c++)
+          for (int k = 0; k < 3; k++) {
+            out.lo[k] = fminf(out.lo[k], S.slots[c].lo[k]);
+            out.hi[k] = fmaxf(out.hi[k], S.slots[c].hi[k]);
+          }
       }
-      S.tlas[node] = n;
+      S.slots[s] = out;
     }
   }
 }
@@ -121,33 +118,36 @@ bool make_scene(const b2_model_desc* m, const double* xpos, const double* xmat,
   // topology from (possibly different) poses, boxes refit to the actual poses: exactly what the
   // runtime does for worlds other than the one the topology was built on
   if (!build_geom_topology(hm, topo_xpos ? topo_xpos : xpos, topo_xmat ? topo_xmat : xmat,
-                           kPacketStack - 2, S.topo, err))
+                           kMaxWideDepth, S.topo, err))
     return false;
   host_refit(S);
   return true;
 }
 
 void fill_params(const EmuScene& S, CastParams& p) {
-  p.tlas = S.tlas.data();
+  p.wslots = S.slots.data();
+  p.wnodes = S.topo.nodes.data();
   p.pose = S.pose.data();
   p.gstat = S.gstat.data();
   p.plane_ids = S.hm.plane_ids.data();
   p.mesh = S.meshes.infos.data();
   p.mnodes = S.meshes.nodes.data();
   p.mtris = S.meshes.tris.data();
-  p.nnode = (int)S.tlas.size();
+  p.nslot = (int)S.slots.size();
+  p.nwnode = (int)S.topo.nodes.size();
   p.ngeom = S.hm.ngeom;
   p.nplane = (int)S.hm.plane_ids.size();
   p.nworld = 1;
 }
 
 void run(const EmuScene& S, CastParams& p, const double o[3], const double* R) {
+  (void)S;
   HostWarp warp;
   const float tcap = p.mode == MODE_MULTIRAY ? f32_up(p.cutoff) : FLT_MAX;
   for (int r = 0; r < p.nray; r++) {
     double l[3], vec[3];
     const bool active = cast_make_ray(p, p.mode, R, r, l, vec);
-    const Hit hit = trace_tile<false>(p, p.tlas, p.pose, active, o, vec, tcap, warp);
+    const Hit hit = trace_tile<false>(p, p.wslots, p.wnodes, p.pose, active, o, vec, tcap, warp);
     cast_epilogue(p, p.mode, 0, r, hit, l);
   }
 }
@@ -210,16 +210,75 @@ int emu_lidar(const b2_model_desc* m, const double* xpos, const double* xmat,
   return 0;
 }
 
-// BVH statistics for tests: node count and max depth of the geom BVH and total mesh nodes
+// BVH statistics for tests: child slots / depth of the wide geom BVH and total mesh nodes
 int emu_bvh_stats(const b2_model_desc* m, const double* xpos, const double* xmat, int mesh_leaf,
-                  int32_t* nnode, int32_t* depth, int64_t* mesh_nodes) {
+                  int32_t* nslot, int32_t* depth, int64_t* mesh_nodes) {
   EmuScene S;
   std::string err;
   if (!make_scene(m, xpos, xmat, nullptr, nullptr, mesh_leaf, S, err)) return -1;
-  *nnode = (int32_t)S.tlas.size();
-  *depth = S.topo.max_depth;
+  *nslot = (int32_t)S.slots.size();
+  *depth = S.topo.depth;
   *mesh_nodes = (int64_t)S.meshes.nodes.size();
   return 0;
+}
+
+// Property check of the tile cone (tests): builds the cone of `n` rays from one origin exactly as
+// trace_tile does (here with a serial reduction) and counts boxes some ray's slab test touches but
+// cone_box rejects.  Must be 0: the collect phase may never drop a box a lane needs.
+int emu_cone_violations(const double pnt[3], const double* vec, int n, const float* boxes,
+                        int nbox) {
+  TileCone tc;
+  float sx = 0, sy = 0, sz = 0;
+  std::vector<float> df((size_t)n * 3);
+  for (int i = 0; i < n; i++) {
+    const float s = (float)dot3(vec + 3 * i, vec + 3 * i);
+    const float inv = rsqrt_f32(s);
+    for (int k = 0; k < 3; k++) df[3 * i + k] = (float)vec[3 * i + k] * inv;
+    sx += df[3 * i];
+    sy += df[3 * i + 1];
+    sz += df[3 * i + 2];
+  }
+  const float an = sqrtf(sx * sx + sy * sy + sz * sz);
+  tc.wide = !(an > 1e-3f);
+  const float ian = tc.wide ? 0.f : 1.0f / an;
+  tc.a[0] = sx * ian;
+  tc.a[1] = sy * ian;
+  tc.a[2] = sz * ian;
+  float cmin = 1.0f;
+  for (int i = 0; i < n; i++)
+    cmin = fminf(cmin, df[3 * i] * tc.a[0] + df[3 * i + 1] * tc.a[1] + df[3 * i + 2] * tc.a[2]);
+  tc.cos_t = fminf(fmaxf(cmin - 8e-6f, -1.0f), 1.0f);
+  if (tc.cos_t < 0.2f) tc.wide = true;
+  tc.sin_t = sqrtf(fmaxf(1.0f - tc.cos_t * tc.cos_t, 0.f)) + 8e-6f;
+  tc.omag = 0.f;
+  for (int k = 0; k < 3; k++) {
+    tc.o[k] = (float)pnt[k];
+    tc.oslack[k] = 2e-6f * fabsf(tc.o[k]) + 1e-30f;
+    tc.omag += fabsf(tc.o[k]);
+  }
+  tc.far2 = INFINITY;
+  int bad = 0;
+  for (int b = 0; b < nbox; b++) {
+    const float* lo = boxes + 6 * b;
+    const float* hi = lo + 3;
+    float key2;
+    const bool keep = cone_box(tc, lo, hi, key2);
+    bool touched = false;
+    for (int i = 0; i < n && !touched; i++) {
+      RayF rf;
+      rayf_setup(rf, pnt, vec + 3 * i);
+      float tn;
+      if (slab_test(rf, lo, hi, FLT_MAX, tn)) {
+        touched = true;
+        // the ordering key must not exceed the true entry distance of any ray
+        const float vlen = sqrtf((float)dot3(vec + 3 * i, vec + 3 * i));
+        const double entry = (double)tn * vlen;
+        if ((double)key2 > entry * entry * (1.0 + 1e-4) + 1e-12) bad++;
+      }
+    }
+    if (touched && !keep) bad++;
+  }
+  return bad;
 }
 
 }  // extern "C"

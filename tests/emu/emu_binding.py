@@ -109,4 +109,16 @@ def bvh_stats(model, poses, world=0, mesh_leaf=2):
     rc = lib().emu_bvh_stats(C.byref(desc), _p(xpos), _p(xmat), mesh_leaf, C.byref(nn), C.byref(dp),
                              C.byref(mn))
     assert rc == 0
-    return {"bvh_nodes": nn.value, "depth": dp.value, "mesh_nodes": mn.value}
+    return {"bvh_slots": nn.value, "depth": dp.value, "mesh_nodes": mn.value}
+
+
+def cone_violations(pnt, vec, boxes) -> int:
+    """number of boxes a ray's slab test touches but the tile cone (built from `vec`) rejects,
+    plus ordering keys that exceed a ray's entry distance.  Must be 0."""
+    pnt = np.ascontiguousarray(pnt, np.float64).reshape(3)
+    vec = np.ascontiguousarray(vec, np.float64).reshape(-1, 3)
+    boxes = np.ascontiguousarray(boxes, np.float32).reshape(-1, 6)
+    L = lib()
+    L.emu_cone_violations.restype = C.c_int
+    L.emu_cone_violations.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int]
+    return L.emu_cone_violations(_p(pnt), _p(vec), vec.shape[0], _p(boxes), boxes.shape[0])

@@ -128,3 +128,28 @@ def test_emu_mesh_leaf_sizes_agree(emu, clutter):
     for leaf in (2, 4):
         out = emu.multiray(cs.model, cs.poses, cs.sensor_pos, vec, bodyexclude=63, mesh_leaf=leaf)
         assert np.array_equal(ref[0], out[0]) and np.array_equal(ref[1], out[1])
+
+
+def test_tile_cone_is_conservative(emu):
+    """collect phase: a box touched by any ray of a tile is never rejected by the tile cone, and
+    its ordering key never exceeds a ray's entry distance (random tiles x random boxes, incl.
+    boxes containing the origin, behind it, huge walls and far-from-origin coordinates)."""
+    rng = np.random.default_rng(11)
+    total = 0
+    for trial in range(60):
+        origin = rng.uniform(-30, 30, 3) * (100.0 if trial % 7 == 0 else 1.0)
+        axis = rng.normal(size=3)
+        axis /= np.linalg.norm(axis)
+        spread = 10 ** rng.uniform(-3, -0.3)          # 0.001 .. 0.5 rad
+        n = 32 if trial % 5 else 7
+        vec = axis[None] + rng.normal(size=(n, 3)) * spread
+        vec *= 10 ** rng.uniform(-2, 2, size=(n, 1))   # non-unit lengths
+        nb = 400
+        cen = origin[None] + rng.normal(size=(nb, 3)) * 10 ** rng.uniform(-1, 1.5, size=(nb, 1))
+        # half of the boxes are placed along the cone so that many are grazed
+        t = 10 ** rng.uniform(-1, 1.5, size=(nb // 2, 1))
+        cen[: nb // 2] = origin[None] + axis[None] * t + rng.normal(size=(nb // 2, 3)) * t * spread * 2
+        half = 10 ** rng.uniform(-2, 1, size=(nb, 3))
+        boxes = np.concatenate([cen - half, cen + half], axis=1).astype(np.float32)
+        total += emu.cone_violations(origin, vec, boxes)
+    assert total == 0
