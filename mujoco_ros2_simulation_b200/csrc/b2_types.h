@@ -97,8 +97,27 @@ enum CastMode : int32_t {
   MODE_CAMERA = 2     // dir from pinhole intrinsics, GL depth epilogue
 };
 
+// Scratch of the split mesh path (K2b-K2d).  K2 appends one PAIR per (ray, mesh geom whose box the
+// ray enters) and one AFFECTED record per ray that has at least one pair; the mesh kernels trace the
+// pairs with full warps, merge the distances with 64-bit atomicMin on the IEEE bit pattern (a
+// non-negative double orders like its bits) and rewrite the outputs of the affected rays.
+struct MeshSplit {
+  int32_t* pair_slot;              // [pair_cap] affected-record slot of the pair's ray
+  int32_t* pair_geom;              // [pair_cap] mesh geom id
+  double* pair_x;                  // [pair_cap] mj_rayMesh result of the pair
+  uint32_t* aff_ray;               // [aff_cap] ray index within the launch (scan * nray + r)
+  unsigned long long* aff_bits;    // [aff_cap] current best distance bits (prim hit or +inf)
+  unsigned long long* aff_prim;    // [aff_cap] distance bits of the primitive-only hit
+  int32_t* aff_prim_id;            // [aff_cap]
+  int32_t* aff_mesh_id;            // [aff_cap] lowest mesh geom id reaching aff_bits
+  int32_t* counters;               // [4] npair, naff, overflow, unused
+  int32_t pair_cap, aff_cap;
+};
+constexpr unsigned long long kInfBits = 0x7ff0000000000000ull;
+
 // Everything one cast launch reads.  Passed by value as a __grid_constant__ kernel parameter.
 struct CastParams {
+  MeshSplit ms;  // used when the launch splits the mesh work off (ms.counters != nullptr)
   // scene mirror
   const WideChild* wslots;  // [nworld][nslot] geom BVH child slots (boxes refit per step)
   const WideNode* wnodes;   // [nwnode] geom BVH topology (node 0 = root)
@@ -120,6 +139,7 @@ struct CastParams {
   float cam_near, cam_far;
   // batch
   int32_t nscan;
+  int32_t scan0;              // index of this launch's first scan in the caller's batch (world mapping)
   const int32_t* scan_world;  // nullable
   const double* spos;         // [nscan*3]
   const double* smat;         // [nscan*9]

@@ -1,0 +1,361 @@
+// cast_kernels.cu -- K2: the ray-cast kernels (sm_100a).
+//
+//   K2  cast_kernel        one warp per tile of 32 rays: planes, warp-cooperative collect over the
+//                          fanout-32 geom BVH (tile_trace.cuh), closed-form fp64 primitive tests,
+//                          fused LaserScan / multiRay / GL-depth epilogue.  Mesh geoms are not
+//                          traced here: each (ray, mesh geom) whose box the ray enters becomes a
+//                          PAIR in a compacted global list (SPLIT = true).
+//   K2b mesh_pairs_kernel  one thread per pair: mj_rayMesh through the per-mesh triangle BVH;
+//                          adjacent pairs come from the same tile and the same mesh, so warps are
+//                          full and coherent.  Distances merge with a 64-bit atomicMin.
+//   K2c mesh_ids_kernel    lowest mesh geom id among the pairs that reached the minimum.
+//   K2d mesh_final_kernel  re-runs the epilogue for the rays a mesh changed.
+//   Launches too small to amortise four kernels, and chunks whose pair list overflowed, use
+//   cast_kernel<SPLIT = false>, which traces meshes in place (same results, slower).
+//
+// Compile with -fmad=false: distances must be bit-identical to the CPU oracle (ray_core.cuh).
+// No tensor cores: nothing here is a dense contraction.
+#include <cuda_runtime.h>
+
+#include "kernels.cuh"
+#include "ray_core.cuh"
+
+namespace b2 {
+
+constexpr int kCastThreads = 256;
+constexpr int kCastWarps = kCastThreads / 32;
+constexpr size_t kStageLimit = 96 * 1024;  // largest geom BVH staged in shared memory per CTA
+constexpr int kMeshThreads = 128;
+
+int cast_tiles_per_scan(int nray) { return (nray + 31) / 32; }
+int cast_threads_per_block() { return kCastThreads; }
+size_t cast_stage_limit_bytes() { return kStageLimit; }
+size_t cast_stage_bytes(int nslot, int nwnode) {
+  return (size_t)nslot * sizeof(WideChild) + (size_t)nwnode * sizeof(WideNode);
+}
+
+// per-warp shared-memory scratch of the cast kernel
+struct WarpScratch {
+  F4 cand_a[kCandCap];       // candidate box lo.xyz + distance key
+  F4 cand_b[kCandCap];       // candidate box hi.xyz + geom id bits
+  int32_t queue[kQueueCap];  // collect frontier
+  int32_t order[kCandCap];   // rank-sorted candidate slots
+};
+
+template <bool SPLIT>
+struct DevWarp {
+  WarpScratch* s;
+  int lane_;
+  int slot;  // affected-record slot of this lane's ray in the current tile (-1: none yet)
+  __device__ __forceinline__ int size() const { return 32; }
+  __device__ __forceinline__ int lane() const { return lane_; }
+  __device__ __forceinline__ unsigned lanemask_lt() const { return (1u << lane_) - 1u; }
+  __device__ __forceinline__ unsigned ballot(bool pred) const {
+    return __ballot_sync(0xffffffffu, pred);
+  }
+  __device__ __forceinline__ bool any(bool pred) const { return __any_sync(0xffffffffu, pred); }
+  __device__ __forceinline__ int popc(unsigned m) const { return __popc(m); }
+  __device__ __forceinline__ void sync() const { __syncwarp(); }
+  __device__ __forceinline__ float sum(float v) const {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+  }
+  __device__ __forceinline__ float min(float v) const {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fminf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+  }
+  __device__ __forceinline__ float max(float v) const {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+  }
+  __device__ __forceinline__ int32_t* queue() const { return s->queue; }
+  __device__ __forceinline__ F4* cand_a() const { return s->cand_a; }
+  __device__ __forceinline__ F4* cand_b() const { return s->cand_b; }
+  __device__ __forceinline__ int32_t* order() const { return s->order; }
+
+  // a mesh geom some lane's ray enters (called by all lanes, g warp-uniform)
+  __device__ __forceinline__ void mesh_pair(const CastParams& p, const GeomPose* pose, int g,
+                                            bool h, Hit& hit, const double pnt[3],
+                                            const double vec[3], float tcap) {
+    if (!SPLIT) {
+      mesh_inline(p, pose, g, h, hit, pnt, vec, tcap);
+      return;
+    }
+    const unsigned m = ballot(h);
+    if (m == 0u) return;
+    const int leader = __ffs(m) - 1;
+    // first pair of a ray: reserve its affected-record slot (warp-aggregated atomics)
+    const unsigned mnew = ballot(h && slot < 0);
+    int abase = 0, pbase = 0;
+    if (lane_ == leader) {
+      if (mnew) abase = atomicAdd(p.ms.counters + 1, __popc(mnew));
+      pbase = atomicAdd(p.ms.counters + 0, __popc(m));
+    }
+    abase = __shfl_sync(0xffffffffu, abase, leader);
+    pbase = __shfl_sync(0xffffffffu, pbase, leader);
+    if (h) {
+      if (slot < 0) slot = abase + __popc(mnew & lanemask_lt());
+      const int idx = pbase + __popc(m & lanemask_lt());
+      if (idx < p.ms.pair_cap && slot < p.ms.aff_cap) {
+        p.ms.pair_slot[idx] = slot;
+        p.ms.pair_geom[idx] = g;
+      } else {
+        p.ms.counters[2] = 1;  // overflow: the clean-up launch recomputes this chunk in place
+      }
+    }
+  }
+};
+
+// ray index of (tile, lane): 8x4 tiles over (scan line, line index) for 3-D sensors, else 32x1
+__device__ __forceinline__ int tile_ray(int tile, int lane, int tiles_x, int tile_w) {
+  if (tiles_x > 0) {
+    const int ty = tile / tiles_x, tx = tile - ty * tiles_x;
+    return (ty * 4 + (lane >> 3)) * tile_w + tx * 8 + (lane & 7);
+  }
+  return tile * 32 + lane;
+}
+
+// the scan's sensor frame and ray r of it (same arithmetic in K2 and in the mesh kernels)
+template <int MODE>
+__device__ __forceinline__ bool scan_ray(const CastParams& p, int scan, int r, double o[3],
+                                         double l[3], double vec[3]) {
+  double R[9];
+#pragma unroll
+  for (int k = 0; k < 3; k++) o[k] = __ldg(p.spos + (size_t)scan * 3 + k);
+  if (MODE != MODE_MULTIRAY) {
+#pragma unroll
+    for (int k = 0; k < 9; k++) R[k] = __ldg(p.smat + (size_t)scan * 9 + k);
+  }
+  return cast_make_ray(p, MODE, R, r, l, vec);
+}
+
+#ifndef B2_CAST_MINBLOCKS
+#define B2_CAST_MINBLOCKS 2
+#endif
+
+struct TileGeom {
+  int tiles_per_block, tiles_per_scan, chunks_per_scan, tiles_x;
+};
+
+// ONLY_IF_OVERFLOW: the clean-up launch -- exits at once unless the split pass overflowed
+template <int MODE, bool STAGE, bool SPLIT, bool ONLY_IF_OVERFLOW>
+__global__ void __launch_bounds__(kCastThreads, B2_CAST_MINBLOCKS)
+    cast_kernel(const __grid_constant__ CastParams p, const TileGeom tg) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  if (ONLY_IF_OVERFLOW) {
+    if (p.ms.counters[2] == 0) return;
+  }
+  WarpScratch* scratch = reinterpret_cast<WarpScratch*>(smem_raw);
+  unsigned char* s_stage = smem_raw + kCastWarps * sizeof(WarpScratch);
+
+  const int warp_id = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int scan = blockIdx.x / tg.chunks_per_scan;
+  const int chunk = blockIdx.x - scan * tg.chunks_per_scan;
+  const int world = p.scan_world ? p.scan_world[scan] : (p.scan0 + scan) % p.nworld;
+
+  // geom BVH of this world: child slots (boxes) + topology, staged in shared memory per CTA
+  const WideChild* wslots = p.wslots + (size_t)world * p.nslot;
+  const WideNode* wnodes = p.wnodes;
+  if (STAGE) {
+    const float4* src = reinterpret_cast<const float4*>(wslots);
+    float4* dst = reinterpret_cast<float4*>(s_stage);
+    for (int i = threadIdx.x; i < p.nslot * 2; i += kCastThreads) dst[i] = __ldg(src + i);
+    int2* ndst = reinterpret_cast<int2*>(s_stage + (size_t)p.nslot * sizeof(WideChild));
+    const int2* nsrc = reinterpret_cast<const int2*>(p.wnodes);
+    for (int i = threadIdx.x; i < p.nwnode; i += kCastThreads) ndst[i] = __ldg(nsrc + i);
+    __syncthreads();
+    wslots = reinterpret_cast<const WideChild*>(s_stage);
+    wnodes = reinterpret_cast<const WideNode*>(ndst);
+  }
+  const GeomPose* pose = p.pose + (size_t)world * p.ngeom;
+
+  DevWarp<SPLIT> warp{scratch + warp_id, lane, -1};
+  const float tcap = (MODE == MODE_MULTIRAY) ? f32_up(p.cutoff) : FLT_MAX;
+
+  for (int t = warp_id; t < tg.tiles_per_block; t += kCastWarps) {
+    const int tile = chunk * tg.tiles_per_block + t;
+    if (tile >= tg.tiles_per_scan) break;  // warp-uniform
+    const int r = tile_ray(tile, lane, tg.tiles_x, p.tile_w);
+    bool active = r < p.nray;
+    const int rr = active ? r : 0;
+
+    // sensor frame: warp-uniform and L1-resident, reloaded per tile so it is not live across
+    // the traversal
+    double o[3], l[3], vec[3];
+    active = scan_ray<MODE>(p, scan, rr, o, l, vec) && active;
+    warp.slot = -1;
+
+    const Hit hit = trace_tile<STAGE>(p, wslots, wnodes, pose, active, o, vec, tcap, warp);
+
+    if (r < p.nray) {
+      if (SPLIT && warp.slot >= 0 && warp.slot < p.ms.aff_cap) {
+        const int s = warp.slot;
+        const unsigned long long bits =
+            hit.dist < 0 ? kInfBits : (unsigned long long)__double_as_longlong(hit.dist);
+        p.ms.aff_ray[s] = (uint32_t)((size_t)scan * p.nray + r);
+        p.ms.aff_bits[s] = bits;
+        p.ms.aff_prim[s] = bits;
+        p.ms.aff_prim_id[s] = hit.id;
+        p.ms.aff_mesh_id[s] = INT32_MAX;
+      }
+      double le[3] = {0.0, 0.0, 0.0};
+      if (MODE == MODE_LIDAR && p.xyz != nullptr) {  // reloaded, not kept live across the trace
+#pragma unroll
+        for (int k = 0; k < 3; k++) le[k] = __ldg(p.local_dir + (size_t)r * 3 + k);
+      }
+      cast_epilogue(p, MODE, scan, r, hit, le);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K2b: one thread per (ray, mesh geom) pair
+// ---------------------------------------------------------------------------------------------
+template <int MODE>
+__global__ void __launch_bounds__(kMeshThreads) mesh_pairs_kernel(const __grid_constant__ CastParams p) {
+  const int npair = ::min(p.ms.counters[0], p.ms.pair_cap);
+  const float tcap = (MODE == MODE_MULTIRAY) ? f32_up(p.cutoff) : FLT_MAX;
+  for (int i = blockIdx.x * kMeshThreads + threadIdx.x; i < npair; i += gridDim.x * kMeshThreads) {
+    const int slot = p.ms.pair_slot[i];
+    const int g = p.ms.pair_geom[i];
+    const uint32_t ray = p.ms.aff_ray[slot];
+    const int scan = (int)(ray / (uint32_t)p.nray), r = (int)(ray - (uint32_t)scan * (uint32_t)p.nray);
+    const int world = p.scan_world ? p.scan_world[scan] : (p.scan0 + scan) % p.nworld;
+    const GeomPose* pose = p.pose + (size_t)world * p.ngeom;
+    double o[3], l[3], vec[3];
+    scan_ray<MODE>(p, scan, r, o, l, vec);
+    // whatever the primitives and the other pairs of this ray have found so far bounds the search
+    const unsigned long long cur = *reinterpret_cast<volatile unsigned long long*>(p.ms.aff_bits + slot);
+    const float tmax =
+        cur == kInfBits ? tcap : fminf(tcap, f32_up(__longlong_as_double((long long)cur)));
+    const double x = mesh_trace(p.mesh, p.mnodes, p.mtris, pose + g, p.gstat + g, o[0], o[1], o[2],
+                                vec[0], vec[1], vec[2], tmax);
+    p.ms.pair_x[i] = x;
+    if (x >= 0) atomicMin(p.ms.aff_bits + slot, (unsigned long long)__double_as_longlong(x));
+  }
+}
+
+// K2c: lowest mesh geom id among the pairs that reached the ray's minimum (A.5 tie rule)
+__global__ void __launch_bounds__(kMeshThreads) mesh_ids_kernel(const __grid_constant__ CastParams p) {
+  const int npair = ::min(p.ms.counters[0], p.ms.pair_cap);
+  for (int i = blockIdx.x * kMeshThreads + threadIdx.x; i < npair; i += gridDim.x * kMeshThreads) {
+    const double x = p.ms.pair_x[i];
+    if (x < 0) continue;
+    const int slot = p.ms.pair_slot[i];
+    if ((unsigned long long)__double_as_longlong(x) == p.ms.aff_bits[slot])
+      atomicMin(p.ms.aff_mesh_id + slot, p.ms.pair_geom[i]);
+  }
+}
+
+// K2d: rays whose closest hit a mesh changed (or tied): rewrite their outputs
+template <int MODE>
+__global__ void __launch_bounds__(kMeshThreads) mesh_final_kernel(const __grid_constant__ CastParams p) {
+  const int naff = ::min(p.ms.counters[1], p.ms.aff_cap);
+  for (int s = blockIdx.x * kMeshThreads + threadIdx.x; s < naff; s += gridDim.x * kMeshThreads) {
+    const int mesh_id = p.ms.aff_mesh_id[s];
+    if (mesh_id == INT32_MAX) continue;  // no mesh reached the minimum: K2's output stands
+    const unsigned long long fin = p.ms.aff_bits[s], prim = p.ms.aff_prim[s];
+    Hit hit;
+    hit.dist = __longlong_as_double((long long)fin);
+    hit.id = fin < prim ? mesh_id : ::min(p.ms.aff_prim_id[s], mesh_id);
+    const uint32_t ray = p.ms.aff_ray[s];
+    const int scan = (int)(ray / (uint32_t)p.nray), r = (int)(ray - (uint32_t)scan * (uint32_t)p.nray);
+    double le[3] = {0.0, 0.0, 0.0};
+    if (MODE == MODE_LIDAR && p.xyz != nullptr) {
+#pragma unroll
+      for (int k = 0; k < 3; k++) le[k] = __ldg(p.local_dir + (size_t)r * 3 + k);
+    }
+    cast_epilogue(p, MODE, scan, r, hit, le);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// launch
+// ---------------------------------------------------------------------------------------------
+template <class K>
+static cudaError_t launch_tile_kernel(K k, const CastParams& p, const TileGeom& tg, unsigned nblocks,
+                                      size_t smem, cudaStream_t stream) {
+  cudaError_t err = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (err != cudaSuccess) return err;
+  // ask for the largest shared-memory carve-out so several CTAs fit next to each other
+  cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout,
+                       cudaSharedmemCarveoutMaxShared);
+  k<<<nblocks, kCastThreads, smem, stream>>>(p, tg);
+  return cudaGetLastError();
+}
+
+template <int MODE>
+static cudaError_t launch_cast_mode(const CastParams& p, bool stage, int tiles_per_block,
+                                    int sm_count, cudaStream_t stream, int* nlaunch) {
+  // 2-D tiling when the sensor is a grid of scan lines
+  TileGeom tg;
+  tg.tiles_x = 0;
+  tg.tiles_per_scan = cast_tiles_per_scan(p.nray);
+  if (p.tile_w > 0 && p.tile_w % 8 == 0 && p.nray % p.tile_w == 0) {
+    const int rows = p.nray / p.tile_w;
+    if (rows >= 4 && rows % 4 == 0) {
+      tg.tiles_x = p.tile_w / 8;
+      tg.tiles_per_scan = tg.tiles_x * (rows / 4);
+    }
+  }
+  if (tiles_per_block < kCastWarps) tiles_per_block = kCastWarps;
+  tg.tiles_per_block = tiles_per_block;
+  tg.chunks_per_scan = (tg.tiles_per_scan + tiles_per_block - 1) / tiles_per_block;
+  const long long nblocks = (long long)p.nscan * tg.chunks_per_scan;
+  if (nblocks <= 0) return cudaSuccess;
+  if (nblocks > 0x7fffffffLL) return cudaErrorInvalidConfiguration;
+  size_t smem = kCastWarps * sizeof(WarpScratch);
+  if (stage) smem += cast_stage_bytes(p.nslot, p.nwnode);
+  const bool split = p.ms.counters != nullptr;
+  cudaError_t err;
+  if (!split) {
+    err = stage ? launch_tile_kernel(cast_kernel<MODE, true, false, false>, p, tg, (unsigned)nblocks,
+                                     smem, stream)
+                : launch_tile_kernel(cast_kernel<MODE, false, false, false>, p, tg,
+                                     (unsigned)nblocks, smem, stream);
+    *nlaunch += 1;
+    return err;
+  }
+  err = cudaMemsetAsync(p.ms.counters, 0, 4 * sizeof(int32_t), stream);
+  if (err != cudaSuccess) return err;
+  err = stage ? launch_tile_kernel(cast_kernel<MODE, true, true, false>, p, tg, (unsigned)nblocks,
+                                   smem, stream)
+              : launch_tile_kernel(cast_kernel<MODE, false, true, false>, p, tg, (unsigned)nblocks,
+                                   smem, stream);
+  if (err != cudaSuccess) return err;
+  const unsigned mgrid = (unsigned)(sm_count * 16);
+  mesh_pairs_kernel<MODE><<<mgrid, kMeshThreads, 0, stream>>>(p);
+  mesh_ids_kernel<<<mgrid, kMeshThreads, 0, stream>>>(p);
+  mesh_final_kernel<MODE><<<mgrid, kMeshThreads, 0, stream>>>(p);
+  err = cudaGetLastError();
+  if (err != cudaSuccess) return err;
+  // clean-up: recompute the chunk in place if the pair list overflowed (exits at once otherwise)
+  err = stage ? launch_tile_kernel(cast_kernel<MODE, true, false, true>, p, tg, (unsigned)nblocks,
+                                   smem, stream)
+              : launch_tile_kernel(cast_kernel<MODE, false, false, true>, p, tg, (unsigned)nblocks,
+                                   smem, stream);
+  *nlaunch += 5;
+  return err;
+}
+
+cudaError_t launch_cast(const CastParams& p, bool stage_tlas, int tiles_per_block, int sm_count,
+                        cudaStream_t stream, int* nlaunch) {
+  if (p.nwnode == 0 || cast_stage_bytes(p.nslot, p.nwnode) > kStageLimit) stage_tlas = false;
+  switch (p.mode) {
+    case MODE_LIDAR:
+      return launch_cast_mode<MODE_LIDAR>(p, stage_tlas, tiles_per_block, sm_count, stream, nlaunch);
+    case MODE_MULTIRAY:
+      return launch_cast_mode<MODE_MULTIRAY>(p, stage_tlas, tiles_per_block, sm_count, stream,
+                                             nlaunch);
+    case MODE_CAMERA:
+      return launch_cast_mode<MODE_CAMERA>(p, stage_tlas, tiles_per_block, sm_count, stream,
+                                           nlaunch);
+    default:
+      return cudaErrorInvalidValue;
+  }
+}
+
+}  // namespace b2

@@ -1,8 +1,7 @@
 // kernels.cu -- hand-written sm_100a kernels of the sensor-readout engine.
 //
 //   K1 refit_kernel           pose packing + bottom-up refit of the per-world geom BVH
-//   K2 cast_kernel            warp-packet BVH traversal, closed-form fp64 leaf tests, fused
-//                             LaserScan / multiRay / GL-depth epilogues
+//   (K2, the ray-cast kernels, live in cast_kernels.cu)
 //   K3 depth_to_cloud_kernel  depth linearise + vertical flip + PointCloud2 projection (streaming)
 //
 // Compile with -fmad=false: distances must be bit-identical to the CPU oracle (see ray_core.cuh).
@@ -13,17 +12,6 @@
 #include "ray_core.cuh"
 
 namespace b2 {
-
-constexpr int kCastThreads = 256;
-constexpr int kCastWarps = kCastThreads / 32;
-constexpr size_t kStageLimit = 96 * 1024;  // largest geom BVH staged in shared memory per CTA
-
-int cast_tiles_per_scan(int nray) { return (nray + 31) / 32; }
-int cast_threads_per_block() { return kCastThreads; }
-size_t cast_stage_limit_bytes() { return kStageLimit; }
-size_t cast_stage_bytes(int nslot, int nwnode) {
-  return (size_t)nslot * sizeof(WideChild) + (size_t)nwnode * sizeof(WideNode);
-}
 
 // =============================================================================================
 // K1: refit
@@ -86,172 +74,6 @@ cudaError_t launch_refit(const RefitParams& p, cudaStream_t stream) {
   while (threads < 128 && threads < p.ngeom * 2) threads *= 2;
   refit_kernel<<<p.nworld, threads, 0, stream>>>(p);
   return cudaGetLastError();
-}
-
-// =============================================================================================
-// K2: cast
-// =============================================================================================
-// per-warp shared-memory scratch of the cast kernel
-struct WarpScratch {
-  F4 cand_a[kCandCap];          // candidate box lo.xyz + distance key
-  F4 cand_b[kCandCap];          // candidate box hi.xyz + geom id bits
-  int32_t queue[kQueueCap];     // collect frontier
-  int32_t order[kCandCap];      // rank-sorted candidate slots
-};
-
-struct DevWarp {
-  WarpScratch* s;
-  int lane_;
-  __device__ __forceinline__ int size() const { return 32; }
-  __device__ __forceinline__ int lane() const { return lane_; }
-  __device__ __forceinline__ unsigned lanemask_lt() const { return (1u << lane_) - 1u; }
-  __device__ __forceinline__ unsigned ballot(bool pred) const {
-    return __ballot_sync(0xffffffffu, pred);
-  }
-  __device__ __forceinline__ bool any(bool pred) const { return __any_sync(0xffffffffu, pred); }
-  __device__ __forceinline__ int popc(unsigned m) const { return __popc(m); }
-  __device__ __forceinline__ void sync() const { __syncwarp(); }
-  __device__ __forceinline__ float sum(float v) const {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    return v;
-  }
-  __device__ __forceinline__ float min(float v) const {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v = fminf(v, __shfl_xor_sync(0xffffffffu, v, o));
-    return v;
-  }
-  __device__ __forceinline__ float max(float v) const {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
-    return v;
-  }
-  __device__ __forceinline__ int32_t* queue() const { return s->queue; }
-  __device__ __forceinline__ F4* cand_a() const { return s->cand_a; }
-  __device__ __forceinline__ F4* cand_b() const { return s->cand_b; }
-  __device__ __forceinline__ int32_t* order() const { return s->order; }
-};
-
-// ray index of (tile, lane): 8x4 tiles over (scan line, line index) for 3-D sensors, else 32x1
-__device__ __forceinline__ int tile_ray(int tile, int lane, int tiles_x, int tile_w) {
-  if (tiles_x > 0) {
-    const int ty = tile / tiles_x, tx = tile - ty * tiles_x;
-    return (ty * 4 + (lane >> 3)) * tile_w + tx * 8 + (lane & 7);
-  }
-  return tile * 32 + lane;
-}
-
-template <int MODE, bool STAGE>
-__global__ void __launch_bounds__(kCastThreads)
-    cast_kernel(const __grid_constant__ CastParams p, const int tiles_per_block,
-                const int tiles_per_scan, const int chunks_per_scan, const int tiles_x) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  WarpScratch* scratch = reinterpret_cast<WarpScratch*>(smem_raw);
-  unsigned char* s_stage = smem_raw + kCastWarps * sizeof(WarpScratch);
-
-  const int warp_id = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int scan = blockIdx.x / chunks_per_scan;
-  const int chunk = blockIdx.x - scan * chunks_per_scan;
-  const int world = p.scan_world ? p.scan_world[scan] : scan % p.nworld;
-
-  // geom BVH of this world: child slots (boxes) + topology, staged in shared memory per CTA
-  const WideChild* wslots = p.wslots + (size_t)world * p.nslot;
-  const WideNode* wnodes = p.wnodes;
-  if (STAGE) {
-    const float4* src = reinterpret_cast<const float4*>(wslots);
-    float4* dst = reinterpret_cast<float4*>(s_stage);
-    for (int i = threadIdx.x; i < p.nslot * 2; i += kCastThreads) dst[i] = __ldg(src + i);
-    int2* ndst = reinterpret_cast<int2*>(s_stage + (size_t)p.nslot * sizeof(WideChild));
-    const int2* nsrc = reinterpret_cast<const int2*>(p.wnodes);
-    for (int i = threadIdx.x; i < p.nwnode; i += kCastThreads) ndst[i] = __ldg(nsrc + i);
-    __syncthreads();
-    wslots = reinterpret_cast<const WideChild*>(s_stage);
-    wnodes = reinterpret_cast<const WideNode*>(ndst);
-  }
-  const GeomPose* pose = p.pose + (size_t)world * p.ngeom;
-
-  DevWarp warp{scratch + warp_id, lane};
-  const float tcap = (MODE == MODE_MULTIRAY) ? f32_up(p.cutoff) : FLT_MAX;
-
-  for (int t = warp_id; t < tiles_per_block; t += kCastWarps) {
-    const int tile = chunk * tiles_per_block + t;
-    if (tile >= tiles_per_scan) break;  // warp-uniform
-    const int r = tile_ray(tile, lane, tiles_x, p.tile_w);
-    bool active = r < p.nray;
-    const int rr = active ? r : 0;
-
-    // sensor frame (warp-uniform, L1-resident): reloaded per tile so it is not live across the
-    // traversal
-    double o[3], R[9], l[3], vec[3];
-#pragma unroll
-    for (int k = 0; k < 3; k++) o[k] = __ldg(p.spos + (size_t)scan * 3 + k);
-    if (MODE != MODE_MULTIRAY) {
-#pragma unroll
-      for (int k = 0; k < 9; k++) R[k] = __ldg(p.smat + (size_t)scan * 9 + k);
-    }
-    active = cast_make_ray(p, MODE, R, rr, l, vec) && active;
-
-    const Hit hit = trace_tile<STAGE>(p, wslots, wnodes, pose, active, o, vec, tcap, warp);
-
-    if (r < p.nray) {
-      double le[3] = {0.0, 0.0, 0.0};
-      if (MODE == MODE_LIDAR && p.xyz != nullptr) {  // reloaded, not kept live across the trace
-#pragma unroll
-        for (int k = 0; k < 3; k++) le[k] = __ldg(p.local_dir + (size_t)r * 3 + k);
-      }
-      cast_epilogue(p, MODE, scan, r, hit, le);
-    }
-  }
-}
-
-template <int MODE>
-static cudaError_t launch_cast_mode(const CastParams& p, bool stage, int tiles_per_block,
-                                    cudaStream_t stream) {
-  // 2-D tiling when the sensor is a grid of scan lines
-  int tiles_x = 0;
-  int tiles_per_scan = cast_tiles_per_scan(p.nray);
-  if (p.tile_w > 0 && p.tile_w % 8 == 0 && p.nray % p.tile_w == 0) {
-    const int rows = p.nray / p.tile_w;
-    if (rows >= 4 && rows % 4 == 0) {
-      tiles_x = p.tile_w / 8;
-      tiles_per_scan = tiles_x * (rows / 4);
-    }
-  }
-  if (tiles_per_block < kCastWarps) tiles_per_block = kCastWarps;
-  const int chunks_per_scan = (tiles_per_scan + tiles_per_block - 1) / tiles_per_block;
-  const long long nblocks = (long long)p.nscan * chunks_per_scan;
-  if (nblocks <= 0) return cudaSuccess;
-  if (nblocks > 0x7fffffffLL) return cudaErrorInvalidConfiguration;
-  size_t smem = kCastWarps * sizeof(WarpScratch);
-  if (stage) smem += cast_stage_bytes(p.nslot, p.nwnode);
-  cudaError_t err;
-  if (stage) {
-    auto k = cast_kernel<MODE, true>;
-    err = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (err != cudaSuccess) return err;
-    k<<<(unsigned)nblocks, kCastThreads, smem, stream>>>(p, tiles_per_block, tiles_per_scan,
-                                                         chunks_per_scan, tiles_x);
-  } else {
-    auto k = cast_kernel<MODE, false>;
-    k<<<(unsigned)nblocks, kCastThreads, smem, stream>>>(p, tiles_per_block, tiles_per_scan,
-                                                         chunks_per_scan, tiles_x);
-  }
-  return cudaGetLastError();
-}
-
-cudaError_t launch_cast(const CastParams& p, bool stage_tlas, int tiles_per_block,
-                        cudaStream_t stream) {
-  if (p.nwnode == 0 || cast_stage_bytes(p.nslot, p.nwnode) > kStageLimit) stage_tlas = false;
-  switch (p.mode) {
-    case MODE_LIDAR:
-      return launch_cast_mode<MODE_LIDAR>(p, stage_tlas, tiles_per_block, stream);
-    case MODE_MULTIRAY:
-      return launch_cast_mode<MODE_MULTIRAY>(p, stage_tlas, tiles_per_block, stream);
-    case MODE_CAMERA:
-      return launch_cast_mode<MODE_CAMERA>(p, stage_tlas, tiles_per_block, stream);
-    default:
-      return cudaErrorInvalidValue;
-  }
 }
 
 // =============================================================================================

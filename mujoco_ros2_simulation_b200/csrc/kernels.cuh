@@ -37,8 +37,9 @@ cudaError_t launch_refit(const RefitParams& p, cudaStream_t stream);
 
 // K2: cast nscan*nray rays.  stage_tlas: copy the world's geom BVH into shared memory per CTA.
 // tiles_per_block: 32-ray tiles one CTA walks through (multiple of the warps per CTA).
-cudaError_t launch_cast(const CastParams& p, bool stage_tlas, int tiles_per_block,
-                        cudaStream_t stream);
+// nlaunch is incremented by the number of kernels enqueued (1, or 5 when the mesh work is split off)
+cudaError_t launch_cast(const CastParams& p, bool stage_tlas, int tiles_per_block, int sm_count,
+                        cudaStream_t stream, int* nlaunch);
 // geometry of the tiling the cast kernel uses for a sensor (for host-side sizing)
 int cast_tiles_per_scan(int nray);
 int cast_threads_per_block();

@@ -38,7 +38,6 @@ namespace b2 {
 #endif
 
 constexpr int kMeshStack = 64;    // mesh-BVH stack entries per lane
-constexpr int kMaxMeshCand = 12;  // deferred mesh candidates per lane
 constexpr int kQueueCap = 160;    // collect frontier (wide node ids) per warp: 1 + 31 * depth
 constexpr int kCandCap = 96;      // candidate geoms per tile between two drains
 
@@ -633,61 +632,33 @@ B2_LEAF double mesh_trace(const MeshInfo* mesh, const BvhNode* mnodes, const Mes
   return x;
 }
 
-// per-lane list of mesh geoms whose box the ray enters; traced after the primitives
-struct MeshCands {
-  float t[kMaxMeshCand];
-  int32_t g[kMaxMeshCand];
-  int n;
-};
-
-B2_HD void mesh_defer(const CastParams& p, const GeomPose* pose, MeshCands& mc, Hit& hit, int g,
-                      float tnear, const double pnt[3], const double vec[3], float tcap) {
-  if (mc.n < kMaxMeshCand) {
-    mc.t[mc.n] = tnear;
-    mc.g[mc.n] = g;
-    mc.n++;
-  } else {  // list full: resolve this one now
-    hit_update(hit,
-               mesh_trace(p.mesh, p.mnodes, p.mtris, pose + g, p.gstat + g, pnt[0], pnt[1], pnt[2],
-                          vec[0], vec[1], vec[2], hit_tmax(hit, tcap)),
-               g);
-  }
-}
-
-B2_HD void mesh_resolve(const CastParams& p, const GeomPose* pose, MeshCands& mc, Hit& hit,
-                        const double pnt[3], const double vec[3], float tcap) {
-  while (mc.n > 0) {  // nearest box first
-    int best = 0;
-    for (int i = 1; i < mc.n; i++)
-      if (mc.t[i] < mc.t[best]) best = i;
-    const float t = mc.t[best];
-    const int g = mc.g[best];
-    mc.n--;
-    mc.t[best] = mc.t[mc.n];
-    mc.g[best] = mc.g[mc.n];
-    const float tmax = hit_tmax(hit, tcap);
-    if (t > tmax) continue;
-    hit_update(hit,
-               mesh_trace(p.mesh, p.mnodes, p.mtris, pose + g, p.gstat + g, pnt[0], pnt[1], pnt[2],
-                          vec[0], vec[1], vec[2], tmax),
-               g);
-  }
-}
-
-// one geom leaf some lane's ray may touch (warp-uniform g); h = this lane's slab test passed
-B2_HD void leaf_visit(const CastParams& p, const GeomPose* pose, int g, bool h, float tnear,
-                      MeshCands& mc, Hit& hit, const double pnt[3], const double vec[3],
-                      float tcap) {
+// One geom leaf some lane's ray may touch (warp-uniform g); h = this lane's slab test passed.
+// Primitives are tested here, all lanes on the same geom type.  Mesh geoms are handed to the warp
+// policy W: the device kernel appends a (ray, mesh geom) PAIR to a compacted global list that the
+// mesh kernels trace afterwards with full warps (mj_rayMesh per pair); the policy of the small /
+// clean-up launches and of the CPU emulation traces the mesh in place.
+template <class W>
+B2_HD void leaf_visit(const CastParams& p, const GeomPose* pose, int g, bool h, Hit& hit,
+                      const double pnt[3], const double vec[3], float tcap, W& warp) {
   const int type = ld_geom_type(p.gstat + g);
-  if (!h) return;
   if (type == GEOM_MESH) {
-    mesh_defer(p, pose, mc, hit, g, tnear, pnt, vec, tcap);
-  } else {
+    warp.mesh_pair(p, pose, g, h, hit, pnt, vec, tcap);
+  } else if (h) {
     hit_update(hit,
                prim_test(type, pose + g, p.gstat + g, pnt[0], pnt[1], pnt[2], vec[0], vec[1],
                          vec[2]),
                g);
   }
+}
+
+// in-place mesh handling (no pair list): used by policies that do not split
+B2_HD void mesh_inline(const CastParams& p, const GeomPose* pose, int g, bool h, Hit& hit,
+                       const double pnt[3], const double vec[3], float tcap) {
+  if (h)
+    hit_update(hit,
+               mesh_trace(p.mesh, p.mnodes, p.mtris, pose + g, p.gstat + g, pnt[0], pnt[1], pnt[2],
+                          vec[0], vec[1], vec[2], hit_tmax(hit, tcap)),
+               g);
 }
 
 // ---------------------------------------------------------------------------------------------

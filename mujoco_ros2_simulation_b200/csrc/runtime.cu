@@ -5,6 +5,7 @@
 // There is no CPU compute path: without a usable CUDA device every entry point returns B2_ERR_CUDA.
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <atomic>
 #include <cmath>
 #include <cstdlib>
@@ -116,6 +117,12 @@ struct b2_scene {
   cudaEvent_t stage_done[2] = {nullptr, nullptr};
   int stage_flip = 0;
   DevBuf<double> d_raw;
+  // scratch of the split mesh path (sized for one chunk of rays)
+  DevBuf<int32_t> d_pair_slot, d_pair_geom, d_aff_prim_id, d_aff_mesh_id, d_counters;
+  DevBuf<double> d_pair_x;
+  DevBuf<uint32_t> d_aff_ray;
+  DevBuf<unsigned long long> d_aff_bits, d_aff_prim;
+  bool has_mesh_geoms = false;
   // scratch for b2_multiray
   DevBuf<double> d_mr_vec, d_mr_dist, d_mr_pnt;
   DevBuf<int32_t> d_mr_id;
@@ -181,8 +188,6 @@ int build_topology(b2_scene* s, const double* xpos, const double* xmat) {
   if (!build_geom_topology(s->hm, xpos, xmat, kMaxWideDepth, w, err))
     return fail(B2_ERR_UNSUPPORTED, err);
   const int nslot = (int)w.slot_link.size(), nwnode = (int)w.nodes.size();
-  if (s->topo_built && nslot != s->nslot)
-    return fail(B2_ERR_INVALID, "internal: slot count changed on rebuild");
   s->nslot = nslot;
   s->nwnode = nwnode;
   s->wide_depth = w.depth;
@@ -264,6 +269,70 @@ void cast_shape(const b2_scene* s, const CastParams& p, bool& stage, int& tiles_
   const int force = env_int("B2_STAGE", -1);
   if (force == 0) stage = false;
   if (force == 1 && bytes > 0 && bytes <= cast_stage_limit_bytes()) stage = true;
+}
+
+// Enqueue one cast (any mode) on `stream`.  Large launches on scenes with mesh geoms are cut into
+// chunks of whole scans so that the scratch of the split mesh path (K2b-K2d) stays bounded; each
+// chunk runs K2 -> K2b -> K2c -> K2d (+ the overflow clean-up guard).
+int run_cast(b2_scene* s, CastParams p, cudaStream_t stream) {
+  if (p.nscan <= 0 || p.nray <= 0) return B2_OK;
+  const long long total = (long long)p.nscan * p.nray;
+  bool split = s->has_mesh_geoms && total >= 65536;
+  const int force = env_int("B2_SPLIT", -1);
+  if (force == 0) split = false;
+  if (force == 1 && s->has_mesh_geoms) split = true;
+  int scans_per_chunk = p.nscan;
+  if (split) {
+    const long long chunk_rays = env_int("B2_CHUNK_MRAYS", 8) * 1000000LL;
+    scans_per_chunk = (int)std::max(1LL, std::min((long long)p.nscan, chunk_rays / p.nray));
+    const size_t aff_cap = (size_t)scans_per_chunk * p.nray;
+    const size_t pair_cap = std::min<size_t>(2 * aff_cap + 1024, 0x7fffffff);
+    if (aff_cap > 0x7fffffff) return fail(B2_ERR_INVALID, "scan too large for the split mesh path");
+    B2_CUDA(s->d_pair_slot.reserve(pair_cap));
+    B2_CUDA(s->d_pair_geom.reserve(pair_cap));
+    B2_CUDA(s->d_pair_x.reserve(pair_cap));
+    B2_CUDA(s->d_aff_ray.reserve(aff_cap));
+    B2_CUDA(s->d_aff_bits.reserve(aff_cap));
+    B2_CUDA(s->d_aff_prim.reserve(aff_cap));
+    B2_CUDA(s->d_aff_prim_id.reserve(aff_cap));
+    B2_CUDA(s->d_aff_mesh_id.reserve(aff_cap));
+    B2_CUDA(s->d_counters.reserve(4));
+    p.ms.pair_slot = s->d_pair_slot.ptr;
+    p.ms.pair_geom = s->d_pair_geom.ptr;
+    p.ms.pair_x = s->d_pair_x.ptr;
+    p.ms.aff_ray = s->d_aff_ray.ptr;
+    p.ms.aff_bits = s->d_aff_bits.ptr;
+    p.ms.aff_prim = s->d_aff_prim.ptr;
+    p.ms.aff_prim_id = s->d_aff_prim_id.ptr;
+    p.ms.aff_mesh_id = s->d_aff_mesh_id.ptr;
+    p.ms.counters = s->d_counters.ptr;
+    p.ms.pair_cap = (int32_t)pair_cap;
+    p.ms.aff_cap = (int32_t)aff_cap;
+  } else {
+    p.ms = MeshSplit{};
+  }
+  const CastParams base = p;
+  for (int s0 = 0; s0 < base.nscan; s0 += scans_per_chunk) {
+    const int ns = std::min(scans_per_chunk, base.nscan - s0);
+    const size_t roff = (size_t)s0 * base.nray;
+    p.nscan = ns;
+    p.scan_world = base.scan_world ? base.scan_world + s0 : nullptr;
+    p.spos = base.spos + 3 * (size_t)s0;
+    p.smat = base.smat ? base.smat + 9 * (size_t)s0 : nullptr;
+    p.ranges = base.ranges ? base.ranges + roff : nullptr;
+    p.geomid = base.geomid ? base.geomid + roff : nullptr;
+    p.dist = base.dist ? base.dist + roff : nullptr;
+    p.xyz = base.xyz ? base.xyz + 3 * roff : nullptr;
+    p.gl_depth = base.gl_depth ? base.gl_depth + roff : nullptr;
+    p.scan0 = base.scan0 + s0;  // scans without a world table map to world (scan0 + s) % nworld
+    bool stage;
+    int tpb;
+    cast_shape(s, p, stage, tpb);
+    int nl = 0;
+    B2_CUDA(launch_cast(p, stage, tpb, s->sm_count, stream, &nl));
+    g_launches += nl;
+  }
+  return B2_OK;
 }
 
 }  // namespace
@@ -373,6 +442,7 @@ int b2_scene_create(const b2_model_desc* m, int32_t nworld, int32_t device, void
     for (int k = 0; k < 3; k++) gs[g].size[k] = m->geom_size[3 * g + k];
     gs[g].type = m->geom_type[g];
     gs[g].dataid = m->geom_dataid[g];
+    if (m->geom_type[g] == GEOM_MESH) s->has_mesh_geoms = true;
     if (m->geom_type[g] == GEOM_PLANE)
       hm.plane_ids.push_back((int32_t)g);
     else
@@ -416,6 +486,15 @@ int b2_scene_destroy(b2_scene* s) {
   s->d_refit_slots.release();
   s->d_level_start.release();
   s->d_raw.release();
+  s->d_pair_slot.release();
+  s->d_pair_geom.release();
+  s->d_pair_x.release();
+  s->d_aff_ray.release();
+  s->d_aff_bits.release();
+  s->d_aff_prim.release();
+  s->d_aff_prim_id.release();
+  s->d_aff_mesh_id.release();
+  s->d_counters.release();
   s->d_mr_vec.release();
   s->d_mr_dist.release();
   s->d_mr_pnt.release();
@@ -607,12 +686,7 @@ static int lidar_launch(b2_lidar* l, int32_t nscan, const int32_t* d_world, cons
   p.geomid = d_geomid;
   p.dist = d_dist;
   p.xyz = d_xyz;
-  bool stage;
-  int tpb;
-  cast_shape(s, p, stage, tpb);
-  B2_CUDA(launch_cast(p, stage, tpb, stream));
-  g_launches++;
-  return B2_OK;
+  return run_cast(s, p, stream);
 }
 
 int b2_lidar_cast_device(b2_lidar* l, int32_t nscan, const int32_t* d_scan_world,
@@ -730,11 +804,10 @@ int b2_multiray(b2_scene* s, int32_t world, const double pnt[3], const double* v
   p.smat = nullptr;
   p.geomid = s->d_mr_id.ptr;
   p.dist = s->d_mr_dist.ptr;
-  bool stage;
-  int tpb;
-  cast_shape(s, p, stage, tpb);
-  B2_CUDA(launch_cast(p, stage, tpb, s->stream));
-  g_launches++;
+  {
+    int rc = run_cast(s, p, s->stream);
+    if (rc != B2_OK) return rc;
+  }
   B2_CUDA(cudaMemcpyAsync(dist, s->d_mr_dist.ptr, (size_t)nray * sizeof(double),
                           cudaMemcpyDeviceToHost, s->stream));
   if (geomid)
@@ -914,12 +987,7 @@ int b2_camera_render_depth_device(b2_camera* c, int32_t ncam, const int32_t* d_c
   p.spos = d_cam_pos;
   p.smat = d_cam_mat;
   p.gl_depth = d_gl_depth;
-  bool stage;
-  int tpb;
-  cast_shape(s, p, stage, tpb);
-  B2_CUDA(launch_cast(p, stage, tpb, c->stream));
-  g_launches++;
-  return B2_OK;
+  return run_cast(s, p, c->stream);
 }
 
 }  // extern "C"

@@ -12,7 +12,8 @@
 //      test of the (warp-uniform) geom type.  The loop ends as soon as no lane can improve.
 //      If the candidate list fills up before the frontier is empty, it is drained early and the
 //      collect continues with the tightened distance bound (incoherent tiles stay correct);
-//   4. mesh geoms a lane's ray enters are deferred and traced per lane through the mesh BVH.
+//   4. mesh geoms a lane's ray enters are not traced here: the warp policy appends (ray, mesh
+//      geom) pairs to a compacted list and separate mesh kernels trace them with full warps.
 #ifndef B2_TILE_TRACE_CUH
 #define B2_TILE_TRACE_CUH
 
@@ -103,8 +104,6 @@ B2_HD Hit trace_tile(const CastParams& p, const WideChild* wslots, const WideNod
 
   RayF rf;
   rayf_setup(rf, pnt, vec);
-  MeshCands mc;
-  mc.n = 0;
 
   // 2. tile cone: axis = mean unit direction, half-angle = largest deviation (+ slack)
   TileCone tc;
@@ -222,15 +221,13 @@ B2_HD Hit trace_tile(const CastParams& p, const WideChild* wslots, const WideNod
       float tn = 0.f;
       const bool h = need && slab_test(rf, lo, hi, hit_tmax(hit, tcap), tn);
       if (!warp.any(h)) continue;
-      leaf_visit(p, pose, f32_as_int(b.w), h, tn, mc, hit, pnt, vec, tcap);
+      leaf_visit(p, pose, f32_as_int(b.w), h, hit, pnt, vec, tcap, warp);
     }
     nc = 0;
     warp.sync();
     if (nq > 0) tc.far2 = warp.max(active ? lane_lim2(hit, tcap, vlen_up) : 0.f);
   }
 
-  // 4. deferred meshes, nearest box first, each lane on its own
-  mesh_resolve(p, pose, mc, hit, pnt, vec, tcap);
   return hit;
 }
 

@@ -38,6 +38,11 @@ struct HostWarp {
   F4* cand_a() { return cand_a_; }
   F4* cand_b() { return cand_b_; }
   int32_t* order() { return order_; }
+  // the emulation traces meshes in place (the device's clean-up / small-launch policy)
+  void mesh_pair(const CastParams& p, const GeomPose* pose, int g, bool h, Hit& hit,
+                 const double pnt[3], const double vec[3], float tcap) {
+    mesh_inline(p, pose, g, h, hit, pnt, vec, tcap);
+  }
 };
 
 struct EmuScene {
