@@ -84,6 +84,12 @@ struct DevWarp {
       mesh_inline(p, pose, g, h, hit, pnt, vec, tcap);
       return;
     }
+    // mj_rayMesh's own pre-test (ray vs the geom_size box, fp64): a ray that misses it returns -1
+    // upstream, so it needs no pair.  Roughly halves the pair list (the world AABB of a rotated
+    // box is loose) and all lanes test the same geom here.
+    if (h)
+      h = prim_test(GEOM_BOX, pose + g, p.gstat + g, pnt[0], pnt[1], pnt[2], vec[0], vec[1],
+                    vec[2]) >= 0;
     const unsigned m = ballot(h);
     if (m == 0u) return;
     const int leader = __ffs(m) - 1;
@@ -214,27 +220,132 @@ __global__ void __launch_bounds__(kCastThreads, B2_CAST_MINBLOCKS)
 // ---------------------------------------------------------------------------------------------
 // K2b: one thread per (ray, mesh geom) pair
 // ---------------------------------------------------------------------------------------------
+//
+// Persistent "while-while" traversal (Aila & Laine style): every lane owns one pair at a time and
+// refills itself from a global work counter when its pair is finished, so lanes with short
+// traversals do not idle behind long ones.  Each outer round runs (1) refill, (2) inner nodes until
+// the lane reaches a leaf, (3) the fp64 triangle tests of that leaf -- so the expensive triangle
+// code runs with most lanes active instead of whenever a single lane happens to hit a leaf.
+// The pair already passed mj_rayMesh's box pre-test in K2, so no post-test is needed here.
 template <int MODE>
 __global__ void __launch_bounds__(kMeshThreads) mesh_pairs_kernel(const __grid_constant__ CastParams p) {
   const int npair = ::min(p.ms.counters[0], p.ms.pair_cap);
   const float tcap = (MODE == MODE_MULTIRAY) ? f32_up(p.cutoff) : FLT_MAX;
-  for (int i = blockIdx.x * kMeshThreads + threadIdx.x; i < npair; i += gridDim.x * kMeshThreads) {
-    const int slot = p.ms.pair_slot[i];
-    const int g = p.ms.pair_geom[i];
-    const uint32_t ray = p.ms.aff_ray[slot];
-    const int scan = (int)(ray / (uint32_t)p.nray), r = (int)(ray - (uint32_t)scan * (uint32_t)p.nray);
-    const int world = p.scan_world ? p.scan_world[scan] : (p.scan0 + scan) % p.nworld;
-    const GeomPose* pose = p.pose + (size_t)world * p.ngeom;
-    double o[3], l[3], vec[3];
-    scan_ray<MODE>(p, scan, r, o, l, vec);
-    // whatever the primitives and the other pairs of this ray have found so far bounds the search
-    const unsigned long long cur = *reinterpret_cast<volatile unsigned long long*>(p.ms.aff_bits + slot);
-    const float tmax =
-        cur == kInfBits ? tcap : fminf(tcap, f32_up(__longlong_as_double((long long)cur)));
-    const double x = mesh_trace(p.mesh, p.mnodes, p.mtris, pose + g, p.gstat + g, o[0], o[1], o[2],
-                                vec[0], vec[1], vec[2], tmax);
-    p.ms.pair_x[i] = x;
-    if (x >= 0) atomicMin(p.ms.aff_bits + slot, (unsigned long long)__double_as_longlong(x));
+  const int lane = threadIdx.x & 31;
+  const unsigned lt = (1u << lane) - 1u;
+  constexpr int32_t kDone = kEmptyChild;
+
+  bool have = false;
+  int pair = 0, slot = 0;
+  double lpnt[3], lvec[3], b0[3], b1[3], x = -1;
+  RayF rf;
+  float tmax = 0.f;
+  const BvhNode* nodes = nullptr;
+  const MeshTri* tris = nullptr;
+  int32_t cur = kDone;
+  int32_t stack[kMeshStack];
+  float stack_t[kMeshStack];
+  int sp = 0;
+
+  for (;;) {
+    // (1) refill: idle lanes take the next pairs; wait until a quarter of the warp is idle so the
+    //     per-pair setup (ray_map, basis, reciprocals) does not run for one lane at a time
+    const unsigned idle = __ballot_sync(0xffffffffu, !have);
+    if (idle == 0xffffffffu || __popc(idle) >= 8) {
+      const int leader = __ffs(idle) - 1;
+      int base = 0;
+      if (lane == leader) base = atomicAdd(p.ms.counters + 3, __popc(idle));
+      base = __shfl_sync(0xffffffffu, base, leader);
+      if (!have) {
+        pair = base + __popc(idle & lt);
+        if (pair < npair) {
+          slot = p.ms.pair_slot[pair];
+          const int g = p.ms.pair_geom[pair];
+          const uint32_t ray = p.ms.aff_ray[slot];
+          const int scan = (int)(ray / (uint32_t)p.nray);
+          const int r = (int)(ray - (uint32_t)scan * (uint32_t)p.nray);
+          const int world = p.scan_world ? p.scan_world[scan] : (p.scan0 + scan) % p.nworld;
+          const GeomPose P = ld_pose(p.pose + (size_t)world * p.ngeom + g);
+          double o[3], l[3], vec[3];
+          scan_ray<MODE>(p, scan, r, o, l, vec);
+          ray_map(P, o, vec, lpnt, lvec);
+          mesh_ray_basis(lvec, b0, b1);
+          rayf_setup(rf, lpnt, lvec);
+          const MeshInfo mi = p.mesh[p.gstat[g].dataid];
+          nodes = p.mnodes + mi.node_base;
+          tris = p.mtris + mi.tri_base;
+          // what the primitives and the other pairs of this ray found so far bounds the search
+          const unsigned long long best =
+              *reinterpret_cast<volatile unsigned long long*>(p.ms.aff_bits + slot);
+          tmax = best == kInfBits ? tcap : fminf(tcap, f32_up(__longlong_as_double((long long)best)));
+          x = -1;
+          sp = 0;
+          cur = 0;
+          have = true;
+        }
+      }
+    }
+    if (!__any_sync(0xffffffffu, have)) break;
+
+    // (2) inner nodes until this lane stands on a leaf (cur < 0) or has nothing left (kDone)
+    while (have && cur >= 0) {
+      const BvhNode n = ld_node(nodes + cur);
+      float t0, t1;
+      const bool h0 = n.c0 != kEmptyChild && slab_test(rf, n.lo0, n.hi0, tmax, t0);
+      const bool h1 = n.c1 != kEmptyChild && slab_test(rf, n.lo1, n.hi1, tmax, t1);
+      if (h0 && h1) {
+        const bool first0 = t0 <= t1;
+        if (sp < kMeshStack) {
+          stack[sp] = first0 ? n.c1 : n.c0;
+          stack_t[sp] = first0 ? t1 : t0;
+          sp++;
+        }
+        cur = first0 ? n.c0 : n.c1;
+      } else if (h0) {
+        cur = n.c0;
+      } else if (h1) {
+        cur = n.c1;
+      } else {
+        cur = kDone;
+        while (sp > 0) {
+          --sp;
+          if (stack_t[sp] <= tmax) {
+            cur = stack[sp];
+            break;
+          }
+        }
+      }
+    }
+
+    // (3) the leaf's triangles (fp64, ref: engine_ray.c ray_triangle)
+    if (have && cur != kDone) {
+      const int32_t payload = ~cur;
+      const int first = payload >> 2, cnt = (payload & 3) + 1;
+#pragma unroll 1
+      for (int i = 0; i < cnt; i++) {
+        const MeshTri tr = ld_tri(tris + first + i);
+        const double sol = ray_triangle(tr.v0, tr.v1, tr.v2, lpnt, lvec, b0, b1);
+        if (sol >= 0 && (x < 0 || sol < x)) {
+          x = sol;
+          tmax = fminf(tmax, f32_up(sol));
+        }
+      }
+      cur = kDone;
+      while (sp > 0) {
+        --sp;
+        if (stack_t[sp] <= tmax) {
+          cur = stack[sp];
+          break;
+        }
+      }
+    }
+
+    // (4) pair finished: publish
+    if (have && cur == kDone) {
+      p.ms.pair_x[pair] = x;
+      if (x >= 0) atomicMin(p.ms.aff_bits + slot, (unsigned long long)__double_as_longlong(x));
+      have = false;
+    }
   }
 }
 
