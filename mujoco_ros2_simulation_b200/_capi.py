@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libb2sense.so")
+LIB_PATH = os.environ.get("B2_LIB_PATH") or os.path.join(_HERE, "libb2sense.so")  # override: A/B builds
 
 i32p = C.POINTER(C.c_int32)
 f64p = C.POINTER(C.c_double)

@@ -227,8 +227,12 @@ __global__ void __launch_bounds__(kCastThreads, B2_CAST_MINBLOCKS)
 // the lane reaches a leaf, (3) the fp64 triangle tests of that leaf -- so the expensive triangle
 // code runs with most lanes active instead of whenever a single lane happens to hit a leaf.
 // The pair already passed mj_rayMesh's box pre-test in K2, so no post-test is needed here.
+#ifndef B2_MESH_MINBLOCKS
+#define B2_MESH_MINBLOCKS 4
+#endif
 template <int MODE>
-__global__ void __launch_bounds__(kMeshThreads) mesh_pairs_kernel(const __grid_constant__ CastParams p) {
+__global__ void __launch_bounds__(kMeshThreads, B2_MESH_MINBLOCKS)
+    mesh_pairs_kernel(const __grid_constant__ CastParams p) {
   const int npair = ::min(p.ms.counters[0], p.ms.pair_cap);
   const float tcap = (MODE == MODE_MULTIRAY) ? f32_up(p.cutoff) : FLT_MAX;
   const int lane = threadIdx.x & 31;

@@ -283,7 +283,9 @@ int run_cast(b2_scene* s, CastParams p, cudaStream_t stream) {
   if (force == 1 && s->has_mesh_geoms) split = true;
   int scans_per_chunk = p.nscan;
   if (split) {
-    const long long chunk_rays = env_int("B2_CHUNK_MRAYS", 8) * 1000000LL;
+    // measured on B200 (profiles/r01_sweeps.txt): 8M rays/chunk 5.0, 32M 5.4, whole launch 5.6
+    // Grays/s -- fewer, longer kernels lose less in launch gaps and tails; scratch is 68 B/ray
+    const long long chunk_rays = env_int("B2_CHUNK_MRAYS", 144) * 1000000LL;
     scans_per_chunk = (int)std::max(1LL, std::min((long long)p.nscan, chunk_rays / p.nray));
     const size_t aff_cap = (size_t)scans_per_chunk * p.nray;
     const size_t pair_cap = std::min<size_t>(2 * aff_cap + 1024, 0x7fffffff);
