@@ -264,6 +264,15 @@ WideBvh collapse_wide(const BuiltBvh& bvh2) {
     int32_t wide_id;
     int depth;
   };
+  // geoms under every BVH2 node (children always have a larger index than their parent)
+  std::vector<int> leaves(bvh2.nodes.size(), 0);
+  for (int i = (int)bvh2.nodes.size() - 1; i >= 0; i--) {
+    const BvhNode& n = bvh2.nodes[(size_t)i];
+    int c = 0;
+    if (n.c0 != kEmptyChild) c += n.c0 >= 0 ? leaves[(size_t)n.c0] : 1;
+    if (n.c1 != kEmptyChild) c += n.c1 >= 0 ? leaves[(size_t)n.c1] : 1;
+    leaves[(size_t)i] = c;
+  }
   std::vector<Pending> todo;
   out.nodes.push_back(WideNode{0, 0});
   todo.push_back({0, 0, 1});
@@ -279,10 +288,18 @@ WideBvh collapse_wide(const BuiltBvh& bvh2) {
       if (n.c1 != kEmptyChild) items.push_back({n.c1, child_area(n, 1)});
     };
     add_children(cur.bvh2_node);
+    // A subtree of <= 32 geoms becomes ONE flat node (a full round of the collect: one lane per
+    // geom).  Above that level only children that are themselves too big for one node are opened,
+    // so inner nodes point at a few fat clusters instead of 32 thin ones: fewer collect rounds per
+    // tile and fuller warps in each.
+    const bool flat = leaves[(size_t)cur.bvh2_node] <= kWideFanout;
     while ((int)items.size() < kWideFanout) {
       int best = -1;
-      for (int i = 0; i < (int)items.size(); i++)
-        if (items[i].link >= 0 && (best < 0 || items[i].area > items[best].area)) best = i;
+      for (int i = 0; i < (int)items.size(); i++) {
+        if (items[i].link < 0) continue;
+        if (!flat && leaves[(size_t)items[i].link] <= kWideFanout) continue;
+        if (best < 0 || items[i].area > items[best].area) best = i;
+      }
       if (best < 0) break;
       const int32_t b2n = items[best].link;
       items.erase(items.begin() + best);

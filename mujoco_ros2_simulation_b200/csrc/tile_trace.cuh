@@ -156,18 +156,13 @@ B2_HD Hit trace_tile(const CastParams& p, const WideChild* wslots, const WideNod
   while (nq > 0 || nc > 0) {
     // 3. COLLECT while there is room for one more node's worth of geoms
     while (nq > 0 && nc <= kCandCap - kWideFanout) {
-      // pop nodes off the frontier while their children still fit into one round of <= 32 slots
-      // (nodes hold ~16 children on average, so most rounds test two or three nodes at once);
-      // `order` is free during the collect and holds the round's slot list
-      int total = 0;
-      while (nq > 0) {
-        const WideNode wn = wnodes[queue[nq - 1]];
-        if (total > 0 && total + wn.count > kWideFanout) break;
-        for (int k = warp.lane(); k < wn.count; k += L) order[total + k] = wn.first + k;
-        total += wn.count;
-        nq--;
-      }
-      warp.sync();  // slot list complete; popped queue entries may be overwritten below
+      // one node per round (packing several half-full nodes into one round was measured slower:
+      // the bookkeeping cost more than the idle lanes, profiles/r01h)
+      const int32_t node = queue[nq - 1];
+      warp.sync();  // everybody has read the top before it is overwritten
+      nq--;
+      const WideNode wn = wnodes[node];
+      const int total = wn.count;
       // one lane per child slot (a 1-lane emulated warp walks the slots in turn)
       for (int base = 0; base < total; base += L) {
         const int k = base + warp.lane();
@@ -176,7 +171,7 @@ B2_HD Hit trace_tile(const CastParams& p, const WideChild* wslots, const WideNod
         WideChild ch;
         ch.link = 0;
         if (k < total) {
-          ch = ld_wslot<STAGE>(wslots + order[k]);
+          ch = ld_wslot<STAGE>(wslots + wn.first + k);
           pass = cone_box(tc, ch.lo, ch.hi, key2);
         }
         const bool inner = pass && ch.link >= 0;
