@@ -4,6 +4,7 @@
 #include <algorithm>
 #include <cfloat>
 #include <cmath>
+#include <cstdlib>
 #include <numeric>
 
 namespace b2 {
@@ -288,11 +289,15 @@ WideBvh collapse_wide(const BuiltBvh& bvh2) {
       if (n.c1 != kEmptyChild) items.push_back({n.c1, child_area(n, 1)});
     };
     add_children(cur.bvh2_node);
-    // A subtree of <= 32 geoms becomes ONE flat node (a full round of the collect: one lane per
-    // geom).  Above that level only children that are themselves too big for one node are opened,
-    // so inner nodes point at a few fat clusters instead of 32 thin ones: fewer collect rounds per
-    // tile and fuller warps in each.
-    const bool flat = leaves[(size_t)cur.bvh2_node] <= kWideFanout;
+    // Default ("thin"): every node is opened greedily to 32 children, so the root of a ~500-geom
+    // scene points at 32 clusters of ~16 geoms.  B2_FAT_CLUSTERS=1 instead keeps subtrees of <= 32
+    // geoms as single flat nodes (fewer, fuller collect rounds) -- measured 2 % slower on B200
+    // (profiles/r01_sweeps.txt: 5.49 vs 5.60 Grays/s): the finer cull of thin clusters wins.
+    static const bool fat_clusters = [] {
+      const char* v = std::getenv("B2_FAT_CLUSTERS");
+      return v ? std::atoi(v) != 0 : false;
+    }();
+    const bool flat = !fat_clusters || leaves[(size_t)cur.bvh2_node] <= kWideFanout;
     while ((int)items.size() < kWideFanout) {
       int best = -1;
       for (int i = 0; i < (int)items.size(); i++) {

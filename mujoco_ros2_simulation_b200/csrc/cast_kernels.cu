@@ -38,6 +38,7 @@ size_t cast_stage_bytes(int nslot, int nwnode) {
 struct WarpScratch {
   F4 cand_a[kCandCap];       // candidate box lo.xyz + distance key
   F4 cand_b[kCandCap];       // candidate box hi.xyz + geom id bits
+  RayState st[kGroupTiles * 32];  // per-ray state of the group between the phases
   int32_t queue[kQueueCap];  // collect frontier
   int32_t order[kCandCap];   // rank-sorted candidate slots
 };
@@ -75,6 +76,9 @@ struct DevWarp {
   __device__ __forceinline__ F4* cand_a() const { return s->cand_a; }
   __device__ __forceinline__ F4* cand_b() const { return s->cand_b; }
   __device__ __forceinline__ int32_t* order() const { return s->order; }
+  __device__ __forceinline__ RayState* ray_state() const { return s->st; }
+  __device__ __forceinline__ void set_slot(int v) { slot = v; }
+  __device__ __forceinline__ int get_slot() const { return slot; }
 
   // a mesh geom some lane's ray enters (called by all lanes, g warp-uniform)
   __device__ __forceinline__ void mesh_pair(const CastParams& p, const GeomPose* pose, int g,
@@ -146,6 +150,49 @@ struct TileGeom {
   int tiles_per_block, tiles_per_scan, chunks_per_scan, tiles_x;
 };
 
+// ray generator of one group: tile t of the group, this lane's ray.  The sensor frame is
+// warp-uniform and L1-resident; it is reloaded on every call so that nothing but the ray itself
+// is live across the traversal.
+template <int MODE>
+struct GroupGen {
+  const CastParams& p;
+  const TileGeom& tg;
+  int scan, tile0, lane;
+  __device__ __forceinline__ bool operator()(int t, double vec[3]) const {
+    const int r = tile_ray(tile0 + t, lane, tg.tiles_x, p.tile_w);
+    const bool in = r < p.nray;
+    double o[3], l[3];
+    return scan_ray<MODE>(p, scan, in ? r : 0, o, l, vec) && in;
+  }
+};
+
+// result sink of one group: the split path's affected record, then the fused epilogue
+template <int MODE, bool SPLIT>
+struct GroupEpi {
+  const CastParams& p;
+  const TileGeom& tg;
+  int scan, tile0, lane;
+  __device__ __forceinline__ void operator()(int t, const Hit& hit, int slot) const {
+    const int r = tile_ray(tile0 + t, lane, tg.tiles_x, p.tile_w);
+    if (r >= p.nray) return;
+    if (SPLIT && slot >= 0 && slot < p.ms.aff_cap) {
+      const unsigned long long bits =
+          hit.dist < 0 ? kInfBits : (unsigned long long)__double_as_longlong(hit.dist);
+      p.ms.aff_ray[slot] = (uint32_t)((size_t)scan * p.nray + r);
+      p.ms.aff_bits[slot] = bits;
+      p.ms.aff_prim[slot] = bits;
+      p.ms.aff_prim_id[slot] = hit.id;
+      p.ms.aff_mesh_id[slot] = INT32_MAX;
+    }
+    double le[3] = {0.0, 0.0, 0.0};
+    if (MODE == MODE_LIDAR && p.xyz != nullptr) {
+#pragma unroll
+      for (int k = 0; k < 3; k++) le[k] = __ldg(p.local_dir + (size_t)r * 3 + k);
+    }
+    cast_epilogue(p, MODE, scan, r, hit, le);
+  }
+};
+
 // ONLY_IF_OVERFLOW: the clean-up launch -- exits at once unless the split pass overflowed
 template <int MODE, bool STAGE, bool SPLIT, bool ONLY_IF_OVERFLOW>
 __global__ void __launch_bounds__(kCastThreads, B2_CAST_MINBLOCKS)
@@ -181,39 +228,17 @@ __global__ void __launch_bounds__(kCastThreads, B2_CAST_MINBLOCKS)
   DevWarp<SPLIT> warp{scratch + warp_id, lane, -1};
   const float tcap = (MODE == MODE_MULTIRAY) ? f32_up(p.cutoff) : FLT_MAX;
 
-  for (int t = warp_id; t < tg.tiles_per_block; t += kCastWarps) {
-    const int tile = chunk * tg.tiles_per_block + t;
-    if (tile >= tg.tiles_per_scan) break;  // warp-uniform
-    const int r = tile_ray(tile, lane, tg.tiles_x, p.tile_w);
-    bool active = r < p.nray;
-    const int rr = active ? r : 0;
-
-    // sensor frame: warp-uniform and L1-resident, reloaded per tile so it is not live across
-    // the traversal
-    double o[3], l[3], vec[3];
-    active = scan_ray<MODE>(p, scan, rr, o, l, vec) && active;
-    warp.slot = -1;
-
-    const Hit hit = trace_tile<STAGE>(p, wslots, wnodes, pose, active, o, vec, tcap, warp);
-
-    if (r < p.nray) {
-      if (SPLIT && warp.slot >= 0 && warp.slot < p.ms.aff_cap) {
-        const int s = warp.slot;
-        const unsigned long long bits =
-            hit.dist < 0 ? kInfBits : (unsigned long long)__double_as_longlong(hit.dist);
-        p.ms.aff_ray[s] = (uint32_t)((size_t)scan * p.nray + r);
-        p.ms.aff_bits[s] = bits;
-        p.ms.aff_prim[s] = bits;
-        p.ms.aff_prim_id[s] = hit.id;
-        p.ms.aff_mesh_id[s] = INT32_MAX;
-      }
-      double le[3] = {0.0, 0.0, 0.0};
-      if (MODE == MODE_LIDAR && p.xyz != nullptr) {  // reloaded, not kept live across the trace
+  // each warp walks groups of kGroupTiles consecutive tiles of this CTA's chunk
+  for (int t = warp_id * kGroupTiles; t < tg.tiles_per_block; t += kCastWarps * kGroupTiles) {
+    const int tile0 = chunk * tg.tiles_per_block + t;
+    if (tile0 >= tg.tiles_per_scan) break;  // warp-uniform
+    const int nt = ::min(kGroupTiles, ::min(tg.tiles_per_block - t, tg.tiles_per_scan - tile0));
+    double o[3];
 #pragma unroll
-        for (int k = 0; k < 3; k++) le[k] = __ldg(p.local_dir + (size_t)r * 3 + k);
-      }
-      cast_epilogue(p, MODE, scan, r, hit, le);
-    }
+    for (int k = 0; k < 3; k++) o[k] = __ldg(p.spos + (size_t)scan * 3 + k);
+    const GroupGen<MODE> gen{p, tg, scan, tile0, lane};
+    const GroupEpi<MODE, SPLIT> epi{p, tg, scan, tile0, lane};
+    trace_group<STAGE>(p, wslots, wnodes, pose, nt, o, tcap, warp, gen, epi);
   }
 }
 
@@ -229,6 +254,9 @@ __global__ void __launch_bounds__(kCastThreads, B2_CAST_MINBLOCKS)
 // The pair already passed mj_rayMesh's box pre-test in K2, so no post-test is needed here.
 #ifndef B2_MESH_MINBLOCKS
 #define B2_MESH_MINBLOCKS 4
+#endif
+#ifndef B2_MESH_REFILL
+#define B2_MESH_REFILL 16  // idle lanes per warp that trigger a refill (2..16 measured: 16 best)
 #endif
 template <int MODE>
 __global__ void __launch_bounds__(kMeshThreads, B2_MESH_MINBLOCKS)
@@ -255,7 +283,7 @@ __global__ void __launch_bounds__(kMeshThreads, B2_MESH_MINBLOCKS)
     // (1) refill: idle lanes take the next pairs; wait until a quarter of the warp is idle so the
     //     per-pair setup (ray_map, basis, reciprocals) does not run for one lane at a time
     const unsigned idle = __ballot_sync(0xffffffffu, !have);
-    if (idle == 0xffffffffu || __popc(idle) >= 8) {
+    if (idle == 0xffffffffu || __popc(idle) >= B2_MESH_REFILL) {
       const int leader = __ffs(idle) - 1;
       int base = 0;
       if (lane == leader) base = atomicAdd(p.ms.counters + 3, __popc(idle));

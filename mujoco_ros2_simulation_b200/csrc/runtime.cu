@@ -258,14 +258,16 @@ void cast_shape(const b2_scene* s, const CastParams& p, bool& stage, int& tiles_
   const int warps = cast_threads_per_block() / 32;
   const long long tiles = (long long)cast_tiles_per_scan(p.nray) * p.nscan;
   const long long want_blocks = (long long)s->sm_count * 16;
+  // a warp walks groups of 4 tiles: the unit of work of a CTA is warps * 4 tiles
+  const int unit = warps * 4;
   long long tpb = tiles / want_blocks;
-  tpb = (tpb / warps) * warps;
-  if (tpb < warps) tpb = warps;
-  if (tpb > 8 * warps) tpb = 8 * warps;
+  tpb = (tpb / unit) * unit;
+  if (tpb < unit) tpb = unit;
+  if (tpb > 2 * unit) tpb = 2 * unit;
   tiles_per_block = env_int("B2_TILES_PER_BLOCK", (int)tpb);
   const size_t bytes = cast_stage_bytes(p.nslot, p.nwnode);
   stage = bytes > 0 && bytes <= cast_stage_limit_bytes() &&
-          (tiles_per_block >= 4 * warps || bytes <= 4096);
+          (tiles_per_block >= 2 * unit || bytes <= 4096);
   const int force = env_int("B2_STAGE", -1);
   if (force == 0) stage = false;
   if (force == 1 && bytes > 0 && bytes <= cast_stage_limit_bytes()) stage = true;

@@ -1,29 +1,42 @@
-// tile_trace.cuh -- warp-cooperative traversal of the wide geom BVH for one tile of rays
+// tile_trace.cuh -- warp-cooperative traversal of the wide geom BVH for a GROUP of ray tiles
 // (included at the end of ray_core.cuh; same host/device rules).
 //
-// One warp = one tile of up to 32 rays that share an origin.
-//   1. planes (kept outside the BVH) are tested first: their hit bounds the search distance;
-//   2. COLLECT: the warp walks the fanout-32 geom BVH once for the whole tile.  Every round pops one
-//      node and tests ALL its children at once, one lane per child slot, against the tile's
-//      bounding cone and against the farthest distance any lane still needs; surviving inner
-//      children go to a small frontier queue, surviving geoms to a shared-memory candidate list;
-//   3. DRAIN: candidates are rank-sorted by their distance from the origin and visited in that
-//      order by all lanes together: per-lane conservative slab test, then the closed-form fp64
-//      test of the (warp-uniform) geom type.  The loop ends as soon as no lane can improve.
-//      If the candidate list fills up before the frontier is empty, it is drained early and the
-//      collect continues with the tightened distance bound (incoherent tiles stay correct);
-//   4. mesh geoms a lane's ray enters are not traced here: the warp policy appends (ray, mesh
-//      geom) pairs to a compacted list and separate mesh kernels trace them with full warps.
+// One warp owns a group of up to kGroupTiles tiles of 32 rays (one ray per lane per tile) that
+// share an origin, e.g. 32 azimuths x 4 scan lines of a spinning lidar.
+//   A. per tile: generate the ray, test the planes (kept outside the BVH: their hit bounds the
+//      search distance), accumulate the group's bounding cone.  Per-ray state (best distance, geom
+//      id, mesh slot) lives in shared memory between the phases, not in registers;
+//   B. COLLECT once for the whole group: the warp walks the fanout-32 geom BVH; every round pops a
+//      node and tests ALL its children at once, one lane per child slot, against the group cone and
+//      against the farthest distance any ray of the group still needs; surviving inner children go
+//      to a small frontier queue, surviving geoms to a shared-memory candidate list, which is then
+//      rank-sorted by distance from the origin.  (One collect per tile cost half of the kernel's
+//      instructions; neighbouring tiles see almost the same clusters -- profiles/r01.)
+//   C. DRAIN per tile: the ray is regenerated and the candidates are visited nearest first by all
+//      lanes together: per-lane conservative slab test, then the closed-form fp64 test of the
+//      (warp-uniform) geom type; the loop ends as soon as no lane can improve.  If the candidate
+//      list fills up before the frontier is empty it is drained early and the collect continues
+//      with the tightened distance bound (incoherent groups stay correct, just slower);
+//   D. mesh geoms a ray enters are not traced here: the warp policy appends (ray, mesh geom) pairs
+//      to a compacted list and separate mesh kernels trace them with full warps;
+//   E. epilogue per tile from the shared-memory state.
 #ifndef B2_TILE_TRACE_CUH
 #define B2_TILE_TRACE_CUH
 
 namespace b2 {
 
 constexpr int kMaxWideDepth = 5;  // queue: every round pops 1 node and pushes <= 32
+constexpr int kGroupTiles = 4;    // tiles per collect
+
+struct B2_ALIGN(16) RayState {
+  double dist;   // best distance so far (< 0: none)
+  int32_t id;    // its geom
+  int32_t slot;  // affected-record slot of the split mesh path (-1: none)
+};
 
 // ---------------------------------------------------------------------------------------------
-// tile cone vs box (conservative).  The cone (apex o, unit axis a, half-angle theta) contains
-// every ray of the tile; a box is kept if its bounding sphere may touch the cone and its nearest
+// group cone vs box (conservative).  The cone (apex o, unit axis a, half-angle theta) contains
+// every ray of the group; a box is kept if its bounding sphere may touch the cone and its nearest
 // point is not farther than any lane still searches.  key2 = squared distance from the apex to
 // the box, rounded down (ordering key of the candidate list).
 // ---------------------------------------------------------------------------------------------
@@ -77,161 +90,218 @@ B2_HD float lane_lim2(const Hit& hit, float tcap, float vlen_up) {
   return l * l * (1.0f + 1e-6f);
 }
 
+// unit direction (float) and |vec| rounded up; false if |vec| is outside the float range
+B2_HD bool unit_dir(const double vec[3], float df[3], float& vlen_up) {
+  const float s = (float)dot3(vec, vec);
+  if (!(s > 1e-30f && s < 1e30f)) return false;
+  const float inv = rsqrt_f32(s);
+  df[0] = (float)vec[0] * inv;
+  df[1] = (float)vec[1] * inv;
+  df[2] = (float)vec[2] * inv;
+  vlen_up = s * inv * (1.0f + 4e-6f);
+  return true;
+}
+
 // ---------------------------------------------------------------------------------------------
-// one ray of a warp tile.  Every lane of the warp must call trace_tile together (lanes without a
-// ray pass active = false); all rays of the tile share the origin pnt.
+// One group of nt <= kGroupTiles tiles.  Every lane of the warp must call trace_group together.
+//   gen(t, vec) -> bool   generates this lane's ray of tile t (false: no ray / degenerate)
+//   epi(t, hit, slot)     consumes the result of this lane's ray of tile t
+// All rays of the group share the origin pnt.
 //   wslots : this world's child slots (shared memory when STAGE), wnodes: topology (same)
 // ---------------------------------------------------------------------------------------------
-template <bool STAGE, class W>
-B2_HD Hit trace_tile(const CastParams& p, const WideChild* wslots, const WideNode* wnodes,
-                     const GeomPose* pose, bool active, const double pnt[3], const double vec[3],
-                     float tcap, W& warp) {
-  Hit hit;
-  hit.dist = -1;
-  hit.id = -1;
-
-  // 1. planes
-  for (int i = 0; i < p.nplane; i++) {
-    const int g = p.plane_ids[i];
-    if (ld_u8(p.elim + g)) continue;
-    if (active)
-      hit_update(hit,
-                 prim_test(GEOM_PLANE, pose + g, p.gstat + g, pnt[0], pnt[1], pnt[2], vec[0],
-                           vec[1], vec[2]),
-                 g);
-  }
-  if (p.nwnode == 0 || !warp.any(active)) return hit;
-
-  RayF rf;
-  rayf_setup(rf, pnt, vec);
-
-  // 2. tile cone: axis = mean unit direction, half-angle = largest deviation (+ slack)
-  TileCone tc;
-  float df[3] = {0.f, 0.f, 0.f};
-  float vlen_up = 0.f;
-  bool odd = false;  // |vec| outside the float range: give up on distance culling for the tile
-  if (active) {
-    const float s = (float)dot3(vec, vec);
-    if (s > 1e-30f && s < 1e30f) {
-      const float inv = rsqrt_f32(s);
-      df[0] = (float)vec[0] * inv;
-      df[1] = (float)vec[1] * inv;
-      df[2] = (float)vec[2] * inv;
-      vlen_up = s * inv * (1.0f + 4e-6f);
-    } else {
-      odd = true;
-    }
-  }
-  odd = warp.any(odd);
-  const float ax = warp.sum(df[0]), ay = warp.sum(df[1]), az = warp.sum(df[2]);
-  const float an = sqrtf(ax * ax + ay * ay + az * az);
-  tc.wide = odd || !(an > 1e-3f);
-  const float ian = tc.wide ? 0.f : 1.0f / an;
-  tc.a[0] = ax * ian;
-  tc.a[1] = ay * ian;
-  tc.a[2] = az * ian;
-  const float cmin = warp.min(active ? df[0] * tc.a[0] + df[1] * tc.a[1] + df[2] * tc.a[2] : 1.0f);
-  tc.cos_t = fminf(fmaxf(cmin - 8e-6f, -1.0f), 1.0f);
-  if (tc.cos_t < 0.2f) tc.wide = true;
-  tc.sin_t = sqrtf(fmaxf(1.0f - tc.cos_t * tc.cos_t, 0.f)) + 8e-6f;
-  tc.omag = 0.f;
-#pragma unroll
-  for (int k = 0; k < 3; k++) {
-    tc.o[k] = (float)pnt[k];
-    tc.oslack[k] = 2e-6f * fabsf(tc.o[k]) + 1e-30f;
-    tc.omag += fabsf(tc.o[k]);
-  }
-  if (odd) vlen_up = INFINITY;
-  tc.far2 = warp.max(active ? lane_lim2(hit, tcap, vlen_up) : 0.f);
-
+template <bool STAGE, class W, class Gen, class Epi>
+B2_HD void trace_group(const CastParams& p, const WideChild* wslots, const WideNode* wnodes,
+                       const GeomPose* pose, int nt, const double pnt[3], float tcap, W& warp,
+                       const Gen& gen, const Epi& epi) {
+  const int L = warp.size(), lane = warp.lane();
+  RayState* st = warp.ray_state();  // [kGroupTiles * L], index t * L + lane
   int32_t* queue = warp.queue();
   F4* cand_a = warp.cand_a();  // lo.xyz, key2
   F4* cand_b = warp.cand_b();  // hi.xyz, geom id bits
   int32_t* order = warp.order();
-  const int L = warp.size();
-  int nq = 1, nc = 0;
-  if (warp.lane() == 0) queue[0] = 0;
-  warp.sync();
+  float* dfbuf = reinterpret_cast<float*>(cand_a);  // unit directions during phase A
 
-  while (nq > 0 || nc > 0) {
-    // 3. COLLECT while there is room for one more node's worth of geoms
-    while (nq > 0 && nc <= kCandCap - kWideFanout) {
-      // one node per round (packing several half-full nodes into one round was measured slower:
-      // the bookkeeping cost more than the idle lanes, profiles/r01h)
-      const int32_t node = queue[nq - 1];
-      warp.sync();  // everybody has read the top before it is overwritten
-      nq--;
-      const WideNode wn = wnodes[node];
-      const int total = wn.count;
-      // one lane per child slot (a 1-lane emulated warp walks the slots in turn)
-      for (int base = 0; base < total; base += L) {
-        const int k = base + warp.lane();
-        bool pass = false;
-        float key2 = 0.f;
-        WideChild ch;
-        ch.link = 0;
-        if (k < total) {
-          ch = ld_wslot<STAGE>(wslots + wn.first + k);
-          pass = cone_box(tc, ch.lo, ch.hi, key2);
-        }
-        const bool inner = pass && ch.link >= 0;
-        const bool leaf = pass && ch.link < 0 && !ld_u8(p.elim + (~ch.link));
-        const unsigned mi = warp.ballot(inner), ml = warp.ballot(leaf);
-        if (inner) {
-          const int pos = nq + warp.popc(mi & warp.lanemask_lt());
-          if (pos < kQueueCap) queue[pos] = ch.link;
-        }
-        if (leaf) {
-          const int pos = nc + warp.popc(ml & warp.lanemask_lt());
-          F4 a, b;
-          a.x = ch.lo[0];
-          a.y = ch.lo[1];
-          a.z = ch.lo[2];
-          a.w = key2;
-          b.x = ch.hi[0];
-          b.y = ch.hi[1];
-          b.z = ch.hi[2];
-          b.w = int_as_f32(~ch.link);
-          cand_a[pos] = a;
-          cand_b[pos] = b;
-        }
-        nq += warp.popc(mi);
-        nc += warp.popc(ml);
-        if (nq > kQueueCap) nq = kQueueCap;  // unreachable: depth is bounded at build time
+  // ---- A. rays, planes, cone accumulation ---------------------------------------------------
+  float sx = 0.f, sy = 0.f, sz = 0.f, lim2max = 0.f;
+  bool odd = false, any_active = false;
+  for (int t = 0; t < nt; t++) {
+    double vec[3];
+    const bool active = gen(t, vec);
+    Hit hit;
+    hit.dist = -1;
+    hit.id = -1;
+    for (int i = 0; i < p.nplane; i++) {
+      const int g = p.plane_ids[i];
+      if (ld_u8(p.elim + g)) continue;
+      if (active)
+        hit_update(hit,
+                   prim_test(GEOM_PLANE, pose + g, p.gstat + g, pnt[0], pnt[1], pnt[2], vec[0],
+                             vec[1], vec[2]),
+                   g);
+    }
+    float df[3] = {0.f, 0.f, 0.f}, vlen_up = 0.f;
+    if (active) {
+      if (unit_dir(vec, df, vlen_up)) {
+        lim2max = fmaxf(lim2max, lane_lim2(hit, tcap, vlen_up));
+      } else {
+        df[0] = df[1] = df[2] = 0.f;
+        odd = true;
       }
-      warp.sync();
     }
-
-    // rank sort by key2 (ties by slot): order[rank] = slot
-    for (int i = warp.lane(); i < nc; i += L) {
-      const float ki = cand_a[i].w;
-      int rank = 0;
-      for (int j = 0; j < nc; j++) {
-        const float kj = cand_a[j].w;
-        rank += (kj < ki || (kj == ki && j < i)) ? 1 : 0;
-      }
-      order[rank] = i;
-    }
-    warp.sync();
-
-    // DRAIN: nearest first; all lanes test the same geom at the same time
-    for (int i = 0; i < nc; i++) {
-      const int slot = order[i];
-      const F4 a = cand_a[slot], b = cand_b[slot];
-      const bool need = active && a.w <= lane_lim2(hit, tcap, vlen_up);
-      if (!warp.any(need)) break;  // sorted: nobody can improve on a later candidate either
-      const float lo[3] = {a.x, a.y, a.z}, hi[3] = {b.x, b.y, b.z};
-      float tn = 0.f;
-      const bool h = need && slab_test(rf, lo, hi, hit_tmax(hit, tcap), tn);
-      if (!warp.any(h)) continue;
-      leaf_visit(p, pose, f32_as_int(b.w), h, hit, pnt, vec, tcap, warp);
-    }
-    nc = 0;
-    warp.sync();
-    if (nq > 0) tc.far2 = warp.max(active ? lane_lim2(hit, tcap, vlen_up) : 0.f);
+    sx += df[0];
+    sy += df[1];
+    sz += df[2];
+    float* d = dfbuf + (size_t)(t * L + lane) * 3;
+    d[0] = df[0];
+    d[1] = df[1];
+    d[2] = df[2];
+    RayState rs;
+    rs.dist = hit.dist;
+    rs.id = hit.id;
+    rs.slot = -1;
+    st[t * L + lane] = rs;
+    any_active = any_active || active;
   }
 
-  return hit;
+  if (p.nwnode != 0 && warp.any(any_active)) {
+    // group cone: axis = mean unit direction, half-angle = largest deviation (+ slack)
+    TileCone tc;
+    odd = warp.any(odd);  // some |vec| outside the float range: no distance / cone culling
+    const float ax = warp.sum(sx), ay = warp.sum(sy), az = warp.sum(sz);
+    const float an = sqrtf(ax * ax + ay * ay + az * az);
+    tc.wide = odd || !(an > 1e-3f);
+    const float ian = tc.wide ? 0.f : 1.0f / an;
+    tc.a[0] = ax * ian;
+    tc.a[1] = ay * ian;
+    tc.a[2] = az * ian;
+    float cmin = 1.0f;
+    for (int t = 0; t < nt; t++) {
+      const float* d = dfbuf + (size_t)(t * L + lane) * 3;
+      const bool has = d[0] != 0.f || d[1] != 0.f || d[2] != 0.f;
+      if (has) cmin = fminf(cmin, d[0] * tc.a[0] + d[1] * tc.a[1] + d[2] * tc.a[2]);
+    }
+    cmin = warp.min(cmin);
+    tc.cos_t = fminf(fmaxf(cmin - 8e-6f, -1.0f), 1.0f);
+    if (tc.cos_t < 0.2f) tc.wide = true;
+    tc.sin_t = sqrtf(fmaxf(1.0f - tc.cos_t * tc.cos_t, 0.f)) + 8e-6f;
+    tc.omag = 0.f;
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+      tc.o[k] = (float)pnt[k];
+      tc.oslack[k] = 2e-6f * fabsf(tc.o[k]) + 1e-30f;
+      tc.omag += fabsf(tc.o[k]);
+    }
+    tc.far2 = odd ? INFINITY : warp.max(lim2max);
+    warp.sync();  // dfbuf (aliasing cand_a) has been consumed
+
+    int nq = 1, nc = 0;
+    if (lane == 0) queue[0] = 0;
+    warp.sync();
+
+    while (nq > 0 || nc > 0) {
+      // ---- B. COLLECT while there is room for one more node's worth of geoms -------------------
+      while (nq > 0 && nc <= kCandCap - kWideFanout) {
+        const int32_t node = queue[nq - 1];
+        warp.sync();  // everybody has read the top before it is overwritten
+        nq--;
+        const WideNode wn = wnodes[node];
+        // one lane per child slot (a 1-lane emulated warp walks the slots in turn)
+        for (int base = 0; base < wn.count; base += L) {
+          const int k = base + lane;
+          bool pass = false;
+          float key2 = 0.f;
+          WideChild ch;
+          ch.link = 0;
+          if (k < wn.count) {
+            ch = ld_wslot<STAGE>(wslots + wn.first + k);
+            pass = cone_box(tc, ch.lo, ch.hi, key2);
+          }
+          const bool inner = pass && ch.link >= 0;
+          const bool leaf = pass && ch.link < 0 && !ld_u8(p.elim + (~ch.link));
+          const unsigned mi = warp.ballot(inner), ml = warp.ballot(leaf);
+          if (inner) {
+            const int pos = nq + warp.popc(mi & warp.lanemask_lt());
+            if (pos < kQueueCap) queue[pos] = ch.link;
+          }
+          if (leaf) {
+            const int pos = nc + warp.popc(ml & warp.lanemask_lt());
+            F4 a, b;
+            a.x = ch.lo[0];
+            a.y = ch.lo[1];
+            a.z = ch.lo[2];
+            a.w = key2;
+            b.x = ch.hi[0];
+            b.y = ch.hi[1];
+            b.z = ch.hi[2];
+            b.w = int_as_f32(~ch.link);
+            cand_a[pos] = a;
+            cand_b[pos] = b;
+          }
+          nq += warp.popc(mi);
+          nc += warp.popc(ml);
+          if (nq > kQueueCap) nq = kQueueCap;  // unreachable: depth is bounded at build time
+        }
+        warp.sync();
+      }
+
+      // rank sort by key2 (ties by slot): order[rank] = slot
+      for (int i = lane; i < nc; i += L) {
+        const float ki = cand_a[i].w;
+        int rank = 0;
+        for (int j = 0; j < nc; j++) {
+          const float kj = cand_a[j].w;
+          rank += (kj < ki || (kj == ki && j < i)) ? 1 : 0;
+        }
+        order[rank] = i;
+      }
+      warp.sync();
+
+      // ---- C. DRAIN per tile: nearest first; all lanes test the same geom at the same time ------
+      lim2max = 0.f;
+      for (int t = 0; t < nt && nc > 0; t++) {
+        double vec[3];
+        const bool active = gen(t, vec);
+        if (!warp.any(active)) continue;
+        RayState rs = st[t * L + lane];
+        Hit hit;
+        hit.dist = rs.dist;
+        hit.id = rs.id;
+        warp.set_slot(rs.slot);
+        RayF rf;
+        rayf_setup(rf, pnt, vec);
+        float df[3], vlen_up = INFINITY;
+        if (active && !odd) unit_dir(vec, df, vlen_up);
+        for (int i = 0; i < nc; i++) {
+          const int slot = order[i];
+          const F4 a = cand_a[slot], b = cand_b[slot];
+          const bool need = active && a.w <= lane_lim2(hit, tcap, vlen_up);
+          if (!warp.any(need)) break;  // sorted: nobody can improve on a later candidate either
+          const float lo[3] = {a.x, a.y, a.z}, hi[3] = {b.x, b.y, b.z};
+          float tn = 0.f;
+          const bool h = need && slab_test(rf, lo, hi, hit_tmax(hit, tcap), tn);
+          if (!warp.any(h)) continue;
+          leaf_visit(p, pose, f32_as_int(b.w), h, hit, pnt, vec, tcap, warp);
+        }
+        rs.dist = hit.dist;
+        rs.id = hit.id;
+        rs.slot = warp.get_slot();
+        st[t * L + lane] = rs;
+        if (active) lim2max = fmaxf(lim2max, lane_lim2(hit, tcap, vlen_up));
+      }
+      nc = 0;
+      warp.sync();
+      if (nq > 0 && !odd) tc.far2 = warp.max(lim2max);
+    }
+  }
+
+  // ---- E. epilogue ------------------------------------------------------------------------------
+  for (int t = 0; t < nt; t++) {
+    const RayState rs = st[t * L + lane];
+    Hit hit;
+    hit.dist = rs.dist;
+    hit.id = rs.id;
+    epi(t, hit, rs.slot);
+  }
 }
 
 }  // namespace b2

@@ -38,6 +38,11 @@ struct HostWarp {
   F4* cand_a() { return cand_a_; }
   F4* cand_b() { return cand_b_; }
   int32_t* order() { return order_; }
+  RayState st_[kGroupTiles];
+  int slot_ = -1;
+  RayState* ray_state() { return st_; }
+  void set_slot(int v) { slot_ = v; }
+  int get_slot() const { return slot_; }
   // the emulation traces meshes in place (the device's clean-up / small-launch policy)
   void mesh_pair(const CastParams& p, const GeomPose* pose, int g, bool h, Hit& hit,
                  const double pnt[3], const double vec[3], float tcap) {
@@ -149,11 +154,19 @@ void run(const EmuScene& S, CastParams& p, const double o[3], const double* R) {
   (void)S;
   HostWarp warp;
   const float tcap = p.mode == MODE_MULTIRAY ? f32_up(p.cutoff) : FLT_MAX;
-  for (int r = 0; r < p.nray; r++) {
-    double l[3], vec[3];
-    const bool active = cast_make_ray(p, p.mode, R, r, l, vec);
-    const Hit hit = trace_tile<false>(p, p.wslots, p.wnodes, p.pose, active, o, vec, tcap, warp);
-    cast_epilogue(p, p.mode, 0, r, hit, l);
+  // groups of kGroupTiles one-ray "tiles": consecutive rays share one collect, as on the device
+  for (int r0 = 0; r0 < p.nray; r0 += kGroupTiles) {
+    const int nt = p.nray - r0 < kGroupTiles ? p.nray - r0 : kGroupTiles;
+    auto gen = [&](int t, double vec[3]) {
+      double l[3];
+      return cast_make_ray(p, p.mode, R, r0 + t, l, vec);
+    };
+    auto epi = [&](int t, const Hit& hit, int) {
+      double l[3], vec[3];
+      cast_make_ray(p, p.mode, R, r0 + t, l, vec);
+      cast_epilogue(p, p.mode, 0, r0 + t, hit, l);
+    };
+    trace_group<false>(p, p.wslots, p.wnodes, p.pose, nt, o, tcap, warp, gen, epi);
   }
 }
 
