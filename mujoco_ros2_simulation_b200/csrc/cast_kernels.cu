@@ -158,11 +158,12 @@ struct GroupGen {
   const CastParams& p;
   const TileGeom& tg;
   int scan, tile0, lane;
-  __device__ __forceinline__ bool operator()(int t, double vec[3]) const {
-    const int r = tile_ray(tile0 + t, lane, tg.tiles_x, p.tile_w);
-    const bool in = r < p.nray;
+  __device__ __forceinline__ bool operator()(int t, double vec[3], int& r) const {
+    const int rr = tile_ray(tile0 + t, lane, tg.tiles_x, p.tile_w);
+    const bool in = rr < p.nray;
+    r = in ? rr : -1;
     double o[3], l[3];
-    return scan_ray<MODE>(p, scan, in ? r : 0, o, l, vec) && in;
+    return scan_ray<MODE>(p, scan, in ? rr : 0, o, l, vec) && in;
   }
 };
 
@@ -172,9 +173,7 @@ struct GroupEpi {
   const CastParams& p;
   const TileGeom& tg;
   int scan, tile0, lane;
-  __device__ __forceinline__ void operator()(int t, const Hit& hit, int slot) const {
-    const int r = tile_ray(tile0 + t, lane, tg.tiles_x, p.tile_w);
-    if (r >= p.nray) return;
+  __device__ __forceinline__ void operator()(int r, const Hit& hit, int slot) const {
     if (SPLIT && slot >= 0 && slot < p.ms.aff_cap) {
       const unsigned long long bits =
           hit.dist < 0 ? kInfBits : (unsigned long long)__double_as_longlong(hit.dist);

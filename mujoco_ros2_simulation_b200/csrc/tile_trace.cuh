@@ -29,9 +29,12 @@ constexpr int kMaxWideDepth = 5;  // queue: every round pops 1 node and pushes <
 constexpr int kGroupTiles = 4;    // tiles per collect
 
 struct B2_ALIGN(16) RayState {
-  double dist;   // best distance so far (< 0: none)
-  int32_t id;    // its geom
-  int32_t slot;  // affected-record slot of the split mesh path (-1: none)
+  double vec[3];  // the ray direction (generated once, in phase A)
+  double dist;    // best distance so far (< 0: none)
+  int32_t id;     // its geom
+  int32_t slot;   // affected-record slot of the split mesh path (-1: none)
+  int32_t r;      // ray index within the scan (-1: this lane has no ray in the tile)
+  int32_t pad;
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -104,8 +107,9 @@ B2_HD bool unit_dir(const double vec[3], float df[3], float& vlen_up) {
 
 // ---------------------------------------------------------------------------------------------
 // One group of nt <= kGroupTiles tiles.  Every lane of the warp must call trace_group together.
-//   gen(t, vec) -> bool   generates this lane's ray of tile t (false: no ray / degenerate)
-//   epi(t, hit, slot)     consumes the result of this lane's ray of tile t
+//   gen(t, vec, r) -> bool  generates this lane's ray of tile t and its index r in the scan
+//                           (false: degenerate ray, traced as a miss; r < 0: no ray at all)
+//   epi(r, hit, slot)       consumes the result of ray r
 // All rays of the group share the origin pnt.
 //   wslots : this world's child slots (shared memory when STAGE), wnodes: topology (same)
 // ---------------------------------------------------------------------------------------------
@@ -126,7 +130,8 @@ B2_HD void trace_group(const CastParams& p, const WideChild* wslots, const WideN
   bool odd = false, any_active = false;
   for (int t = 0; t < nt; t++) {
     double vec[3];
-    const bool active = gen(t, vec);
+    int r = -1;
+    const bool active = gen(t, vec, r);
     Hit hit;
     hit.dist = -1;
     hit.id = -1;
@@ -156,9 +161,14 @@ B2_HD void trace_group(const CastParams& p, const WideChild* wslots, const WideN
     d[1] = df[1];
     d[2] = df[2];
     RayState rs;
+    rs.vec[0] = active ? vec[0] : 0.0;  // an all-zero direction marks a ray that is not traced
+    rs.vec[1] = active ? vec[1] : 0.0;
+    rs.vec[2] = active ? vec[2] : 0.0;
     rs.dist = hit.dist;
     rs.id = hit.id;
     rs.slot = -1;
+    rs.r = r;
+    rs.pad = 0;
     st[t * L + lane] = rs;
     any_active = any_active || active;
   }
@@ -259,10 +269,10 @@ B2_HD void trace_group(const CastParams& p, const WideChild* wslots, const WideN
       // ---- C. DRAIN per tile: nearest first; all lanes test the same geom at the same time ------
       lim2max = 0.f;
       for (int t = 0; t < nt && nc > 0; t++) {
-        double vec[3];
-        const bool active = gen(t, vec);
-        if (!warp.any(active)) continue;
         RayState rs = st[t * L + lane];
+        const double vec[3] = {rs.vec[0], rs.vec[1], rs.vec[2]};
+        const bool active = vec[0] != 0.0 || vec[1] != 0.0 || vec[2] != 0.0;
+        if (!warp.any(active)) continue;
         Hit hit;
         hit.dist = rs.dist;
         hit.id = rs.id;
@@ -300,7 +310,7 @@ B2_HD void trace_group(const CastParams& p, const WideChild* wslots, const WideN
     Hit hit;
     hit.dist = rs.dist;
     hit.id = rs.id;
-    epi(t, hit, rs.slot);
+    if (rs.r >= 0) epi(rs.r, hit, rs.slot);
   }
 }
 

@@ -157,14 +157,15 @@ void run(const EmuScene& S, CastParams& p, const double o[3], const double* R) {
   // groups of kGroupTiles one-ray "tiles": consecutive rays share one collect, as on the device
   for (int r0 = 0; r0 < p.nray; r0 += kGroupTiles) {
     const int nt = p.nray - r0 < kGroupTiles ? p.nray - r0 : kGroupTiles;
-    auto gen = [&](int t, double vec[3]) {
+    auto gen = [&](int t, double vec[3], int& r) {
       double l[3];
-      return cast_make_ray(p, p.mode, R, r0 + t, l, vec);
+      r = r0 + t;
+      return cast_make_ray(p, p.mode, R, r, l, vec);
     };
-    auto epi = [&](int t, const Hit& hit, int) {
+    auto epi = [&](int r, const Hit& hit, int) {
       double l[3], vec[3];
-      cast_make_ray(p, p.mode, R, r0 + t, l, vec);
-      cast_epilogue(p, p.mode, 0, r0 + t, hit, l);
+      cast_make_ray(p, p.mode, R, r, l, vec);
+      cast_epilogue(p, p.mode, 0, r, hit, l);
     };
     trace_group<false>(p, p.wslots, p.wnodes, p.pose, nt, o, tcap, warp, gen, epi);
   }
