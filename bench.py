@@ -40,7 +40,7 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--scans", type=int, default=1024, help="sensor poses per GPU per step")
-    ap.add_argument("--e2e-scans", type=int, default=256, help="sensor poses per e2e step")
+    ap.add_argument("--e2e-scans", type=int, default=1024, help="sensor poses per e2e step")
     ap.add_argument("--ref-scans", type=int, default=4, help="scans per step of the CPU arm")
     ap.add_argument("--cpu-baseline-scans", type=int, default=24)
     ap.add_argument("--no-cpu-baseline", action="store_true")

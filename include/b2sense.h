@@ -174,6 +174,14 @@ int b2_camera_render_depth_device(b2_camera* cam, int32_t ncam, const int32_t* d
                                   const double* d_cam_pos, const double* d_cam_mat,
                                   float* d_gl_depth);
 
+/* Host-pointer convenience for the camera thread when no OpenGL readback exists: ray-casts the GL
+ * depth of ncam camera poses (cam_world NULL: camera i sees world i % nworld), then runs the fused
+ * linearise + flip + cloud step on it.  gl_depth / depth32fc1 / cloud: HOST buffers, each nullable.
+ * Blocking. */
+int b2_camera_render_to_cloud(b2_camera* cam, int32_t ncam, const int32_t* cam_world,
+                              const double* cam_pos, const double* cam_mat, float* gl_depth,
+                              float* depth32fc1, void* cloud);
+
 /* ---- introspection used by bench.py / tests ------------------------------------------------ */
 /* number of kernels this library has launched in this process (all scenes / cameras) */
 long long b2_launch_count(void);

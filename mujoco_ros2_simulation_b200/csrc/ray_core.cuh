@@ -326,18 +326,23 @@ B2_HD double local_box(const double size[3], const double lpnt[3], const double 
   double a0 = lpnt[0], a1 = lpnt[1], a2 = lpnt[2];
   double b0 = lvec[0], b1 = lvec[1], b2 = lvec[2];
   double s0 = size[0], s1 = size[1], s2 = size[2];
-#pragma unroll 1
+  // fully unrolled with the six face divisions issued unconditionally: they are independent, so
+  // their long fp64 latency overlaps (the rolled version stalled on one division at a time).
+  // side * s0 for side = -1 / +1 is exactly -s0 / s0, so the arithmetic is unchanged.
+#pragma unroll
   for (int it = 0; it < 3; it++) {
-    if (fabs(b0) > kMinVal) {
-#pragma unroll 1
-      for (int side = -1; side <= 1; side += 2) {
-        const double sol = (side * s0 - a0) / b0;
-        if (sol >= 0) {
-          const double p0 = a1 + sol * b1;
-          const double p1 = a2 + sol * b2;
-          if (fabs(p0) <= s1 && fabs(p1) <= s2) keep_min(x, sol);
-        }
-      }
+    const bool ok = fabs(b0) > kMinVal;
+    const double solm = (-s0 - a0) / b0;
+    const double solp = (s0 - a0) / b0;
+    if (ok && solm >= 0) {
+      const double p0 = a1 + solm * b1;
+      const double p1 = a2 + solm * b2;
+      if (fabs(p0) <= s1 && fabs(p1) <= s2) keep_min(x, solm);
+    }
+    if (ok && solp >= 0) {
+      const double p0 = a1 + solp * b1;
+      const double p1 = a2 + solp * b2;
+      if (fabs(p0) <= s1 && fabs(p1) <= s2) keep_min(x, solp);
     }
     double t = a0;
     a0 = a1;

@@ -153,6 +153,7 @@ struct b2_camera {
   DevBuf<float> d_in, d_depth, d_cloud;
   DevBuf<uint8_t> d_elim;  // no geom eliminated for the ray-cast depth
   DevBuf<double> d_pos, d_mat;
+  DevBuf<int32_t> d_world;
 };
 
 namespace {
@@ -878,6 +879,7 @@ int b2_camera_destroy(b2_camera* c) {
   c->d_elim.release();
   c->d_pos.release();
   c->d_mat.release();
+  c->d_world.release();
   if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
   delete c;
   return B2_OK;
@@ -992,6 +994,53 @@ int b2_camera_render_depth_device(b2_camera* c, int32_t ncam, const int32_t* d_c
   p.smat = d_cam_mat;
   p.gl_depth = d_gl_depth;
   return run_cast(s, p, c->stream);
+}
+
+int b2_camera_render_to_cloud(b2_camera* c, int32_t ncam, const int32_t* cam_world,
+                              const double* cam_pos, const double* cam_mat, float* gl_depth,
+                              float* depth32fc1, void* cloud) {
+  if (!c) return fail(B2_ERR_INVALID, "null camera");
+  if (!c->scene) return fail(B2_ERR_INVALID, "camera was created without a scene");
+  if (ncam < 0) return fail(B2_ERR_INVALID, "negative ncam");
+  if (ncam == 0) return B2_OK;
+  if (!cam_pos || !cam_mat) return fail(B2_ERR_INVALID, "null camera pose");
+  B2_CUDA(cudaSetDevice(c->device));
+  const size_t npix = (size_t)ncam * c->desc.width * c->desc.height;
+  const size_t pf = (size_t)c->desc.point_step / 4;
+  B2_CUDA(c->d_pos.reserve((size_t)ncam * 3));
+  B2_CUDA(c->d_mat.reserve((size_t)ncam * 9));
+  B2_CUDA(c->d_in.reserve(npix));
+  if (depth32fc1) B2_CUDA(c->d_depth.reserve(npix));
+  if (cloud) B2_CUDA(c->d_cloud.reserve(npix * pf));
+  int32_t* d_world = nullptr;
+  if (cam_world) {
+    B2_CUDA(c->d_world.reserve((size_t)ncam));
+    B2_CUDA(cudaMemcpyAsync(c->d_world.ptr, cam_world, (size_t)ncam * sizeof(int32_t),
+                            cudaMemcpyHostToDevice, c->stream));
+    d_world = c->d_world.ptr;
+  }
+  B2_CUDA(cudaMemcpyAsync(c->d_pos.ptr, cam_pos, (size_t)ncam * 3 * sizeof(double),
+                          cudaMemcpyHostToDevice, c->stream));
+  B2_CUDA(cudaMemcpyAsync(c->d_mat.ptr, cam_mat, (size_t)ncam * 9 * sizeof(double),
+                          cudaMemcpyHostToDevice, c->stream));
+  int rc = b2_camera_render_depth_device(c, ncam, d_world, c->d_pos.ptr, c->d_mat.ptr, c->d_in.ptr);
+  if (rc != B2_OK) return rc;
+  if (depth32fc1 || cloud) {
+    rc = b2_depth_to_cloud_device(c, ncam, c->d_in.ptr, depth32fc1 ? c->d_depth.ptr : nullptr,
+                                  cloud ? c->d_cloud.ptr : nullptr);
+    if (rc != B2_OK) return rc;
+  }
+  if (gl_depth)
+    B2_CUDA(cudaMemcpyAsync(gl_depth, c->d_in.ptr, npix * sizeof(float), cudaMemcpyDeviceToHost,
+                            c->stream));
+  if (depth32fc1)
+    B2_CUDA(cudaMemcpyAsync(depth32fc1, c->d_depth.ptr, npix * sizeof(float),
+                            cudaMemcpyDeviceToHost, c->stream));
+  if (cloud)
+    B2_CUDA(cudaMemcpyAsync(cloud, c->d_cloud.ptr, npix * pf * sizeof(float),
+                            cudaMemcpyDeviceToHost, c->stream));
+  B2_CUDA(cudaStreamSynchronize(c->stream));
+  return B2_OK;
 }
 
 }  // extern "C"

@@ -1,0 +1,299 @@
+// test_api.cpp -- C entry points that let pytest (ctypes) drive the C++ wrapper classes the way
+// MujocoSystemInterface does: construct + register in on_init, init/update in on_activate, close in
+// the destructor (ref:src/mujoco_system_interface.cpp:707-717, 938-939, 467-476).  Only compiled
+// with the stand-in ROS 2 / MuJoCo types of b2_compat.hpp.
+#include <cstring>
+#include <memory>
+#include <mutex>
+#include <sstream>
+#include <string>
+
+#include "mujoco_cameras.hpp"
+#include "mujoco_lidar.hpp"
+
+using namespace mujoco_ros2_control;
+
+namespace
+{
+struct Harness
+{
+  mjModel* m;
+  mjData* d;
+  std::recursive_mutex mtx;
+  rclcpp::Node::SharedPtr node = std::make_shared<rclcpp::Node>();
+  hardware_interface::HardwareInfo info;
+  std::unique_ptr<SceneMirror> mirror;
+  std::unique_ptr<MujocoLidar> lidar;
+  std::unique_ptr<MujocoCameras> cameras;
+  std::string error;
+  double lidar_rate = 5.0, camera_rate = 5.0;  // the interface's defaults (ref :558-560)
+};
+
+// "sensor|key=val;key=val\nsensor2|..." -> HardwareInfo (what the URDF <ros2_control> block carries)
+void parse_info(const char* text, hardware_interface::HardwareInfo& info)
+{
+  std::istringstream in(text ? text : "");
+  std::string line;
+  while (std::getline(in, line))
+  {
+    const auto bar = line.find('|');
+    if (bar == std::string::npos)
+    {
+      continue;
+    }
+    hardware_interface::ComponentInfo c;
+    c.name = line.substr(0, bar);
+    std::istringstream kv(line.substr(bar + 1));
+    std::string item;
+    while (std::getline(kv, item, ';'))
+    {
+      const auto eq = item.find('=');
+      if (eq != std::string::npos)
+      {
+        c.parameters[item.substr(0, eq)] = item.substr(eq + 1);
+      }
+    }
+    info.sensors.push_back(c);
+  }
+}
+}  // namespace
+
+extern "C" {
+
+// on_init part 1: wrappers constructed and registered (no GPU needed)
+void* b2p_create(mjModel* m, mjData* d, const char* hardware_info, double lidar_rate, double camera_rate)
+{
+  auto* h = new Harness();
+  h->m = m;
+  h->d = d;
+  parse_info(hardware_info, h->info);
+  h->lidar_rate = lidar_rate;
+  h->camera_rate = camera_rate;
+  h->lidar = std::make_unique<MujocoLidar>(h->node, &h->mtx, d, m, lidar_rate, nullptr);
+  h->cameras = std::make_unique<MujocoCameras>(h->node, &h->mtx, d, m, camera_rate, nullptr);
+  return h;
+}
+
+int b2p_register(void* hp)
+{
+  auto* h = static_cast<Harness*>(hp);
+  try
+  {
+    h->cameras->register_cameras(h->info);
+  }
+  catch (const std::exception& e)
+  {
+    h->error = std::string("register_cameras: ") + e.what();
+    return -2;
+  }
+  if (!h->lidar->register_lidar(h->info))
+  {
+    h->error = h->lidar->last_error();
+    return -1;  // on_init returns CallbackReturn::FAILURE here (ref :713-717)
+  }
+  return 0;
+}
+
+// on_init part 2 + on_activate: scene mirror + GPU objects (needs a B200)
+int b2p_activate(void* hp)
+{
+  auto* h = static_cast<Harness*>(hp);
+  try
+  {
+    h->mirror = std::make_unique<SceneMirror>(h->m, 0);
+  }
+  catch (const std::exception& e)
+  {
+    h->error = e.what();
+    return -1;
+  }
+  // re-create the wrappers with the mirror, as the interface would construct them
+  h->lidar = std::make_unique<MujocoLidar>(h->node, &h->mtx, h->d, h->m, h->lidar_rate, h->mirror.get());
+  h->cameras = std::make_unique<MujocoCameras>(h->node, &h->mtx, h->d, h->m, h->camera_rate, h->mirror.get());
+  h->cameras->register_cameras(h->info);
+  if (!h->lidar->register_lidar(h->info))
+  {
+    h->error = h->lidar->last_error();
+    return -1;
+  }
+  if (!h->lidar->create_engines())
+  {
+    h->error = h->lidar->last_error();
+    return -2;
+  }
+  if (!h->cameras->create_engines())
+  {
+    h->error = h->cameras->last_error();
+    return -3;
+  }
+  return 0;
+}
+
+// one publish cycle of both wrappers
+int b2p_update(void* hp)
+{
+  auto* h = static_cast<Harness*>(hp);
+  h->lidar->update();
+  if (!h->lidar->last_error().empty())
+  {
+    h->error = h->lidar->last_error();
+    return -1;
+  }
+  h->cameras->update();
+  if (!h->cameras->last_error().empty())
+  {
+    h->error = h->cameras->last_error();
+    return -2;
+  }
+  return 0;
+}
+
+// threads: init() starts them at the publish rate, close() joins them
+int b2p_run_threads(void* hp, int milliseconds)
+{
+  auto* h = static_cast<Harness*>(hp);
+  h->lidar->init();
+  h->cameras->init();
+  std::this_thread::sleep_for(std::chrono::milliseconds(milliseconds));
+  h->lidar->close();
+  h->cameras->close();
+  return 0;
+}
+
+const char* b2p_error(void* hp)
+{
+  return static_cast<Harness*>(hp)->error.c_str();
+}
+
+int b2p_lidar_count(void* hp)
+{
+  return (int)static_cast<Harness*>(hp)->lidar->lidars().size();
+}
+
+// static LaserScan fields + bookkeeping of lidar k
+int b2p_lidar_info(void* hp, int k, int* num_rangefinders, float* f7, int* bodyid, char* frame, char* topic,
+                   int* sensor_indexes, double* local_dir)
+{
+  const auto& l = static_cast<Harness*>(hp)->lidar->lidars().at(k);
+  *num_rangefinders = l.num_rangefinders;
+  const auto& msg = l.laser_scan_msg;
+  f7[0] = msg.angle_min;
+  f7[1] = msg.angle_max;
+  f7[2] = msg.angle_increment;
+  f7[3] = msg.time_increment;
+  f7[4] = msg.scan_time;
+  f7[5] = msg.range_min;
+  f7[6] = msg.range_max;
+  *bodyid = l.bodyid;
+  std::strncpy(frame, msg.header.frame_id.c_str(), 127);
+  std::strncpy(topic, l.scan_pub ? l.scan_pub->get_topic_name().c_str() : "", 127);
+  for (int i = 0; i < l.num_rangefinders; ++i)
+  {
+    sensor_indexes[i] = l.sensor_indexes[i];
+  }
+  std::memcpy(local_dir, l.local_dir.data(), l.local_dir.size() * sizeof(double));
+  return 0;
+}
+
+// last published LaserScan of lidar k
+int b2p_lidar_scan(void* hp, int k, float* ranges, int* n_published, int* n_intensities)
+{
+  const auto& l = static_cast<Harness*>(hp)->lidar->lidars().at(k);
+  const auto& msg = l.scan_pub->last();
+  std::memcpy(ranges, msg.ranges.data(), msg.ranges.size() * sizeof(float));
+  *n_published = (int)l.scan_pub->count();
+  *n_intensities = (int)msg.intensities.size();
+  return (int)msg.ranges.size();
+}
+
+int b2p_camera_count(void* hp)
+{
+  return (int)static_cast<Harness*>(hp)->cameras->cameras().size();
+}
+
+int b2p_camera_info(void* hp, int k, int* wh, double* K, double* R, double* P, int* nd, char* frame,
+                    char* topics /* 4 x 128 */, char* encodings /* 2 x 16 */, int* steps)
+{
+  auto& c = static_cast<Harness*>(hp)->cameras->cameras().at(k);
+  wh[0] = (int)c.width;
+  wh[1] = (int)c.height;
+  std::memcpy(K, c.camera_info.k.data(), 9 * sizeof(double));
+  std::memcpy(R, c.camera_info.r.data(), 9 * sizeof(double));
+  std::memcpy(P, c.camera_info.p.data(), 12 * sizeof(double));
+  *nd = (int)c.camera_info.d.size();
+  std::strncpy(frame, c.frame_name.c_str(), 127);
+  std::strncpy(topics, c.info_topic.c_str(), 127);
+  std::strncpy(topics + 128, c.image_topic.c_str(), 127);
+  std::strncpy(topics + 256, c.depth_topic.c_str(), 127);
+  std::strncpy(topics + 384, c.points_topic.c_str(), 127);
+  std::strncpy(encodings, c.image.encoding.c_str(), 15);
+  std::strncpy(encodings + 16, c.depth_image.encoding.c_str(), 15);
+  steps[0] = (int)c.image.step;
+  steps[1] = (int)c.depth_image.step;
+  steps[2] = (int)c.cloud.point_step;
+  steps[3] = (int)c.cloud.row_step;
+  return 0;
+}
+
+// last published depth image / cloud / raw GL depth of camera k
+int b2p_camera_frames(void* hp, int k, float* gl_depth, float* depth, float* cloud)
+{
+  auto& c = static_cast<Harness*>(hp)->cameras->cameras().at(k);
+  const size_t n = (size_t)c.width * c.height;
+  if (gl_depth)
+  {
+    std::memcpy(gl_depth, c.depth_buffer.data(), n * sizeof(float));
+  }
+  if (depth)
+  {
+    std::memcpy(depth, c.depth_image_pub->last().data.data(), n * sizeof(float));
+  }
+  if (cloud)
+  {
+    std::memcpy(cloud, c.cloud_pub->last().data.data(), n * 12);
+  }
+  return (int)c.depth_image_pub->count();
+}
+
+// feed a GL depth buffer instead of ray casting it (what mjr_readPixels would deliver)
+int b2p_camera_set_gl_depth(void* hp, const float* gl_depth)
+{
+  auto* h = static_cast<Harness*>(hp);
+  h->cameras->set_gl_readback([gl_depth](CameraData& cam) {
+    std::memcpy(cam.depth_buffer.data(), gl_depth, cam.depth_buffer.size() * sizeof(float));
+    for (size_t i = 0; i < cam.image_buffer.size(); ++i)
+    {
+      cam.image_buffer[i] = (uint8_t)(i * 7);  // a recognisable RGB pattern for the flip check
+    }
+    return true;
+  });
+  return 0;
+}
+
+int b2p_camera_rgb(void* hp, int k, uint8_t* rgb_published, uint8_t* rgb_gl)
+{
+  auto& c = static_cast<Harness*>(hp)->cameras->cameras().at(k);
+  std::memcpy(rgb_published, c.image_pub->last().data.data(), c.image.data.size());
+  std::memcpy(rgb_gl, c.image_buffer.data(), c.image_buffer.size());
+  return (int)c.image.data.size();
+}
+
+void b2p_destroy(void* hp)
+{
+  auto* h = static_cast<Harness*>(hp);
+  h->lidar.reset();
+  h->cameras.reset();
+  h->mirror.reset();
+  delete h;
+}
+
+size_t b2p_sizeof_mjmodel()
+{
+  return sizeof(mjModel);
+}
+size_t b2p_sizeof_mjdata()
+{
+  return sizeof(mjData);
+}
+
+}  // extern "C"
