@@ -201,6 +201,14 @@ B2_HD uint8_t ld_u8(const uint8_t* ptr) {
   return *ptr;
 #endif
 }
+// start pulling a record towards L1 (no-op on the host)
+B2_HD void prefetch_l1(const void* ptr) {
+#if B2_ON_DEVICE
+  asm volatile("prefetch.global.L1 [%0];" ::"l"(ptr));
+#else
+  (void)ptr;
+#endif
+}
 
 // ---------------------------------------------------------------------------------------------
 // fp64 closed-form tests (A.3).  Return distance x >= 0 in units of |vec|, or -1.
@@ -380,6 +388,16 @@ B2_LEAF double prim_test(int type, const GeomPose* gp, const GeomStatic* gsp, do
       ssz = gs.size[0] * gs.size[0] + gs.size[1] * gs.size[1] + gs.size[2] * gs.size[2];
     }
     if (ray_sphere(P.pos, ssz, pnt, vec) < 0) return -1;
+  }
+  if (type == GEOM_PLANE && gs.size[0] <= 0 && gs.size[1] <= 0) {
+    // unbounded plane (the usual ground plane, tested for every ray): only the local z components
+    // of ray_map decide; they are computed exactly as ray_map computes them
+    const double d0 = px - P.pos[0], d1 = py - P.pos[1], d2 = pz - P.pos[2];
+    const double lpz = P.mat[2] * d0 + P.mat[5] * d1 + P.mat[8] * d2;
+    const double lvz = P.mat[2] * vx + P.mat[5] * vy + P.mat[8] * vz;
+    if (lvz > -kMinVal) return -1;
+    const double x = -lpz / lvz;
+    return x < 0 ? -1 : x;
   }
   double lpnt[3], lvec[3];
   ray_map(P, pnt, vec, lpnt, lvec);

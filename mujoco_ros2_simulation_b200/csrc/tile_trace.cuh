@@ -244,6 +244,11 @@ B2_HD void trace_group(const CastParams& p, const WideChild* wslots, const WideN
             b.y = ch.hi[1];
             b.z = ch.hi[2];
             b.w = int_as_f32(~ch.link);
+            // the drain will want this geom's pose / size: start the L2 -> L1 fetch now, from all
+            // appending lanes at once, instead of stalling on it one candidate at a time
+            prefetch_l1(pose + (~ch.link));
+            prefetch_l1(reinterpret_cast<const char*>(pose + (~ch.link)) + sizeof(GeomPose) - 1);
+            prefetch_l1(p.gstat + (~ch.link));
             cand_a[pos] = a;
             cand_b[pos] = b;
           }
@@ -281,16 +286,20 @@ B2_HD void trace_group(const CastParams& p, const WideChild* wslots, const WideN
         rayf_setup(rf, pnt, vec);
         float df[3], vlen_up = INFINITY;
         if (active && !odd) unit_dir(vec, df, vlen_up);
+        float tmaxf = hit_tmax(hit, tcap);           // search limit in ray units, rounded up
+        float lim2 = lane_lim2(hit, tcap, vlen_up);  // the same in squared world units
         for (int i = 0; i < nc; i++) {
           const int slot = order[i];
           const F4 a = cand_a[slot], b = cand_b[slot];
-          const bool need = active && a.w <= lane_lim2(hit, tcap, vlen_up);
+          const bool need = active && a.w <= lim2;
           if (!warp.any(need)) break;  // sorted: nobody can improve on a later candidate either
           const float lo[3] = {a.x, a.y, a.z}, hi[3] = {b.x, b.y, b.z};
           float tn = 0.f;
-          const bool h = need && slab_test(rf, lo, hi, hit_tmax(hit, tcap), tn);
+          const bool h = need && slab_test(rf, lo, hi, tmaxf, tn);
           if (!warp.any(h)) continue;
           leaf_visit(p, pose, f32_as_int(b.w), h, hit, pnt, vec, tcap, warp);
+          tmaxf = hit_tmax(hit, tcap);
+          lim2 = lane_lim2(hit, tcap, vlen_up);
         }
         rs.dist = hit.dist;
         rs.id = hit.id;
