@@ -201,9 +201,11 @@ B2_HD uint8_t ld_u8(const uint8_t* ptr) {
   return *ptr;
 #endif
 }
-// start pulling a record towards L1 (no-op on the host)
+// start pulling a record towards L1 (no-op on the host).  Opt-in (-DB2_PREFETCH): prefetching the
+// candidates' poses during the collect measured 0.9 % SLOWER than not doing it
+// (profiles/r01_sweeps.txt: 6.153 vs 6.209 Grays/s), so it is off.
 B2_HD void prefetch_l1(const void* ptr) {
-#if B2_ON_DEVICE
+#if B2_ON_DEVICE && defined(B2_PREFETCH)
   asm volatile("prefetch.global.L1 [%0];" ::"l"(ptr));
 #else
   (void)ptr;
@@ -334,10 +336,15 @@ B2_HD double local_box(const double size[3], const double lpnt[3], const double 
   double a0 = lpnt[0], a1 = lpnt[1], a2 = lpnt[2];
   double b0 = lvec[0], b1 = lvec[1], b2 = lvec[2];
   double s0 = size[0], s1 = size[1], s2 = size[2];
-  // fully unrolled with the six face divisions issued unconditionally: they are independent, so
-  // their long fp64 latency overlaps (the rolled version stalled on one division at a time).
-  // side * s0 for side = -1 / +1 is exactly -s0 / s0, so the arithmetic is unchanged.
+  // The two face divisions of an axis are issued together (independent, so their fp64 latency
+  // overlaps); the axis loop stays rolled unless B2_BOX_UNROLL is set -- the kernel is on the edge
+  // of the instruction cache and the fully unrolled body cost more in fetch stalls than it gained
+  // (profiles/r01l).  side * s0 for side = -1 / +1 is exactly -s0 / s0: arithmetic unchanged.
+#ifdef B2_BOX_UNROLL
 #pragma unroll
+#else
+#pragma unroll 1
+#endif
   for (int it = 0; it < 3; it++) {
     const bool ok = fabs(b0) > kMinVal;
     const double solm = (-s0 - a0) / b0;
@@ -389,6 +396,7 @@ B2_LEAF double prim_test(int type, const GeomPose* gp, const GeomStatic* gsp, do
     }
     if (ray_sphere(P.pos, ssz, pnt, vec) < 0) return -1;
   }
+#ifndef B2_NO_PLANE_FAST
   if (type == GEOM_PLANE && gs.size[0] <= 0 && gs.size[1] <= 0) {
     // unbounded plane (the usual ground plane, tested for every ray): only the local z components
     // of ray_map decide; they are computed exactly as ray_map computes them
@@ -399,6 +407,7 @@ B2_LEAF double prim_test(int type, const GeomPose* gp, const GeomStatic* gsp, do
     const double x = -lpz / lvz;
     return x < 0 ? -1 : x;
   }
+#endif
   double lpnt[3], lvec[3];
   ray_map(P, pnt, vec, lpnt, lvec);
   switch (type) {
