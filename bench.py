@@ -171,6 +171,71 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def other_configs(engine, scenes, torch, dev, stream, nworld3=4096, nworld4=1024):
+    """BASELINE.json configs[2] and configs[3] as secondary measurements (device-resident):
+    cfg3: 4096 replicated arm worlds, one 1024-ray lidar each, all poses refit every step;
+    cfg4: 1024 worlds, a 1024-ray lidar + a 640x480 depth camera (linearise + cloud) each."""
+    out = {}
+    ws = scenes.arm_worlds(nworld=nworld3, n_rays=1024)
+    sc = engine.Scene(ws.model, nworld=nworld3, device=dev.index, stream=stream.cuda_stream)
+    lid = engine.Lidar(sc, ws.lidar)
+    with torch.cuda.stream(stream):
+        xpos = torch.from_numpy(ws.poses.geom_xpos).to(dev)
+        xmat = torch.from_numpy(ws.poses.geom_xmat).to(dev)
+        spos = torch.from_numpy(ws.sensor_pos).to(dev)
+        smat = torch.from_numpy(ws.sensor_mat).to(dev)
+        sw = torch.from_numpy(ws.scan_world).to(dev)
+        rng = torch.empty((nworld3, 1024), dtype=torch.float32, device=dev)
+        gid = torch.empty((nworld3, 1024), dtype=torch.int32, device=dev)
+
+        def step3(n):
+            sc.update_poses_device(xpos[:n], xmat[:n])
+            lid.cast_device(n, spos, smat, sw, ranges=rng, geomid=gid)
+
+        for _ in range(3):
+            step3(nworld3)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 20
+        a.record(stream)
+        for _ in range(reps):
+            step3(nworld3)
+        b.record(stream)
+        stream.synchronize()
+        ms = a.elapsed_time(b) / reps
+        out["cfg3_arm_worlds"] = {"workload": f"{nworld3} worlds x 1024-ray lidar, poses refit per step",
+                                  "grays_per_s": nworld3 * 1024 / (ms * 1e-3) / 1e9, "ms_per_step": ms,
+                                  "hit_fraction": float((gid >= 0).float().mean().item())}
+        # cfg4: the first nworld4 worlds + one depth camera per world
+        cam = engine.DepthCamera(scenes.depth_camera(), scene=sc, device=dev.index)
+        gl = torch.rand((nworld4, 480, 640), dtype=torch.float32, device=dev)
+        dimg = torch.empty_like(gl)
+        cloud = torch.empty((nworld4, 480, 640, 3), dtype=torch.float32, device=dev)
+
+        def step4():
+            step3(nworld4)
+            cam.depth_to_cloud_device(nworld4, gl, dimg, cloud)
+
+        for _ in range(3):
+            step4()
+        reps = 5
+        a.record(stream)
+        for _ in range(reps):
+            step4()
+        b.record(stream)
+        stream.synchronize()
+        ms = a.elapsed_time(b) / reps
+        npx = nworld4 * 480 * 640
+        out["cfg4_depth_plus_lidar"] = {
+            "workload": f"{nworld4} worlds x (640x480 depth -> 32FC1 + cloud, 1024-ray lidar)",
+            "ms_per_step": ms, "gpx_per_s": npx / (ms * 1e-3) / 1e9,
+            "hbm_gbs_algorithmic": (npx * 20 + nworld4 * 1024 * 8) / (ms * 1e-3) / 1e9}
+        del gl, dimg, cloud
+        cam.close()
+    lid.close()
+    sc.close()
+    return out
+
+
 def run_b200(args):
     import torch
     import torch.distributed as dist
@@ -336,10 +401,16 @@ def run_b200(args):
                                   "frac": gbs / peak, "bytes_per_px": 20, "peak_source": how}}
         del gl, dimg, cloud
         cam.close()
+        secondary = {"depth_to_cloud": secondary}
+        try:
+            secondary.update(other_configs(engine, scenes, torch, dev, stream))
+        except Exception as e:  # the headline must not die on a secondary shape
+            secondary["other_configs_error"] = repr(e)
 
     # ---- roofline of the dominant kernel (K2 cast) ------------------------------------------------------
     st = scene.stats()
-    scene_bytes = cs.model.ngeom * (32 + 96) + st["bvh_nodes"] * 64 + st["mesh_nodes"] * 64 + st["mesh_tris"] * 48
+    # GeomStatic 32 + GeomPose 96 per geom, 32 per BVH child slot, 64 per mesh node, 48 per triangle
+    scene_bytes = cs.model.ngeom * (32 + 96) + st["bvh_nodes"] * 32 + st["mesh_nodes"] * 64 + st["mesh_tris"] * 48
     alg_bytes = BYTES_PER_RAY * rays_per_step + scene_bytes
     peak, how = measured_peak()
     achieved = alg_bytes / (ms_kernel * 1e-3) / 1e9
