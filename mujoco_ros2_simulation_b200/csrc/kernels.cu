@@ -49,6 +49,7 @@ __global__ void __launch_bounds__(128) refit_kernel(const RefitParams p) {
         const int g = ~link;
         const GeomStatic gs = p.gstat[g];
         geom_aabb(gs.type, gs.size, pose[g], out.lo, out.hi);
+        out.pad = gs.type;  // travels with the slot so the cast needs no lookup to dispatch
       } else {
         const WideNode wn = p.wnodes[link];
         out.lo[0] = out.lo[1] = out.lo[2] = FLT_MAX;

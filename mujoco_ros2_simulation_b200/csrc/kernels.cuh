@@ -44,7 +44,7 @@ cudaError_t launch_cast(const CastParams& p, bool stage_tlas, int tiles_per_bloc
 int cast_tiles_per_scan(int nray);
 int cast_threads_per_block();
 size_t cast_stage_limit_bytes();
-size_t cast_stage_bytes(int nslot, int nwnode);  // shared memory the staged geom BVH needs
+size_t cast_stage_bytes(int nslot, int nwnode, int ngeom);  // shared memory of the staged geom BVH
 
 // K3: depth linearise + flip + PointCloud2 projection.
 cudaError_t launch_depth_to_cloud(const DepthParams& p, cudaStream_t stream);

@@ -670,9 +670,8 @@ B2_LEAF double mesh_trace(const MeshInfo* mesh, const BvhNode* mnodes, const Mes
 // mesh kernels trace afterwards with full warps (mj_rayMesh per pair); the policy of the small /
 // clean-up launches and of the CPU emulation traces the mesh in place.
 template <class W>
-B2_HD void leaf_visit(const CastParams& p, const GeomPose* pose, int g, bool h, Hit& hit,
+B2_HD void leaf_visit(const CastParams& p, const GeomPose* pose, int g, int type, bool h, Hit& hit,
                       const double pnt[3], const double vec[3], float tcap, W& warp) {
-  const int type = ld_geom_type(p.gstat + g);
   if (type == GEOM_MESH) {
     warp.mesh_pair(p, pose, g, h, hit, pnt, vec, tcap);
   } else if (h) {

@@ -266,7 +266,7 @@ void cast_shape(const b2_scene* s, const CastParams& p, bool& stage, int& tiles_
   if (tpb < unit) tpb = unit;
   if (tpb > 2 * unit) tpb = 2 * unit;
   tiles_per_block = env_int("B2_TILES_PER_BLOCK", (int)tpb);
-  const size_t bytes = cast_stage_bytes(p.nslot, p.nwnode);
+  const size_t bytes = p.nwnode > 0 ? cast_stage_bytes(p.nslot, p.nwnode, p.ngeom) : 0;
   stage = bytes > 0 && bytes <= cast_stage_limit_bytes() &&
           (tiles_per_block >= 2 * unit || bytes <= 4096);
   const int force = env_int("B2_STAGE", -1);
@@ -371,6 +371,8 @@ int b2_scene_create(const b2_model_desc* m, int32_t nworld, int32_t device, void
   *out = nullptr;
   if (m->ngeom < 0 || m->nbody < 1 || m->nmesh < 0 || m->nmat < 0 || nworld < 1)
     return fail(B2_ERR_INVALID, "b2_scene_create: bad counts");
+  if (m->ngeom >= (1 << 24))  // candidate records pack the geom id into 24 bits
+    return fail(B2_ERR_UNSUPPORTED, "b2_scene_create: more than 16M geoms");
   if (m->ngeom > 0 && (!m->geom_type || !m->geom_bodyid || !m->geom_group || !m->geom_matid ||
                        !m->geom_dataid || !m->geom_size || !m->geom_rgba))
     return fail(B2_ERR_INVALID, "b2_scene_create: null geom array");

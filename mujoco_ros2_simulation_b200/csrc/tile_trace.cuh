@@ -115,8 +115,8 @@ B2_HD bool unit_dir(const double vec[3], float df[3], float& vlen_up) {
 // ---------------------------------------------------------------------------------------------
 template <bool STAGE, class W, class Gen, class Epi>
 B2_HD void trace_group(const CastParams& p, const WideChild* wslots, const WideNode* wnodes,
-                       const GeomPose* pose, int nt, const double pnt[3], float tcap, W& warp,
-                       const Gen& gen, const Epi& epi) {
+                       const uint8_t* elim, const GeomPose* pose, int nt, const double pnt[3],
+                       float tcap, W& warp, const Gen& gen, const Epi& epi) {
   const int L = warp.size(), lane = warp.lane();
   RayState* st = warp.ray_state();  // [kGroupTiles * L], index t * L + lane
   int32_t* queue = warp.queue();
@@ -137,7 +137,7 @@ B2_HD void trace_group(const CastParams& p, const WideChild* wslots, const WideN
     hit.id = -1;
     for (int i = 0; i < p.nplane; i++) {
       const int g = p.plane_ids[i];
-      if (ld_u8(p.elim + g)) continue;
+      if (elim[g]) continue;
       if (active)
         hit_update(hit,
                    prim_test(GEOM_PLANE, pose + g, p.gstat + g, pnt[0], pnt[1], pnt[2], vec[0],
@@ -227,7 +227,7 @@ B2_HD void trace_group(const CastParams& p, const WideChild* wslots, const WideN
             pass = cone_box(tc, ch.lo, ch.hi, key2);
           }
           const bool inner = pass && ch.link >= 0;
-          const bool leaf = pass && ch.link < 0 && !ld_u8(p.elim + (~ch.link));
+          const bool leaf = pass && ch.link < 0 && !elim[~ch.link];
           const unsigned mi = warp.ballot(inner), ml = warp.ballot(leaf);
           if (inner) {
             const int pos = nq + warp.popc(mi & warp.lanemask_lt());
@@ -243,7 +243,9 @@ B2_HD void trace_group(const CastParams& p, const WideChild* wslots, const WideN
             b.x = ch.hi[0];
             b.y = ch.hi[1];
             b.z = ch.hi[2];
-            b.w = int_as_f32(~ch.link);
+            // geom id (24 bits) + geom type (from the slot's pad word, written by the refit) so the
+            // drain needs no global load to dispatch
+            b.w = int_as_f32((~ch.link) | (ch.pad << 24));
             // the drain will want this geom's pose / size: start the L2 -> L1 fetch now, from all
             // appending lanes at once, instead of stalling on it one candidate at a time
             prefetch_l1(pose + (~ch.link));
@@ -297,7 +299,8 @@ B2_HD void trace_group(const CastParams& p, const WideChild* wslots, const WideN
           float tn = 0.f;
           const bool h = need && slab_test(rf, lo, hi, tmaxf, tn);
           if (!warp.any(h)) continue;
-          leaf_visit(p, pose, f32_as_int(b.w), h, hit, pnt, vec, tcap, warp);
+          const int32_t gt = f32_as_int(b.w);
+          leaf_visit(p, pose, gt & 0xffffff, gt >> 24, h, hit, pnt, vec, tcap, warp);
           tmaxf = hit_tmax(hit, tcap);
           lim2 = lane_lim2(hit, tcap, vlen_up);
         }

@@ -73,6 +73,7 @@ void host_refit(EmuScene& S) {
       if (link < 0) {
         const int g = ~link;
         geom_aabb(S.gstat[g].type, S.gstat[g].size, S.pose[g], out.lo, out.hi);
+        out.pad = S.gstat[g].type;
       } else {
         const WideNode wn = S.topo.nodes[link];
         for (int k = 0; k < 3; k++) {
@@ -167,7 +168,7 @@ void run(const EmuScene& S, CastParams& p, const double o[3], const double* R) {
       cast_make_ray(p, p.mode, R, r, l, vec);
       cast_epilogue(p, p.mode, 0, r, hit, l);
     };
-    trace_group<false>(p, p.wslots, p.wnodes, p.pose, nt, o, tcap, warp, gen, epi);
+    trace_group<false>(p, p.wslots, p.wnodes, p.elim, p.pose, nt, o, tcap, warp, gen, epi);
   }
 }
 

@@ -107,7 +107,7 @@ def test_cfg5_shape_worlds_on_clutter_topology(oracle):
         assert np.array_equal(out["geomid"][w][::37], g)
     cam = engine.DepthCamera(scenes.depth_camera(160, 120), scene=s)
     R = np.array([[0, 0, -1.0], [-1.0, 0, 0], [0, 1.0, 0]]).reshape(1, 9)
-    cpos = torch.from_numpy(np.tile([[0.0, 0.0, 1.5]], (W, 1))).to(dev)
+    cpos = torch.from_numpy(np.tile([[3.0, 0.0, 1.5]], (W, 1))).to(dev)  # outside the sensor housing
     cmat = torch.from_numpy(np.tile(R, (W, 1))).to(dev)
     cw = torch.arange(W, dtype=torch.int32, device=dev)
     gl = torch.empty((W, 120, 160), dtype=torch.float32, device=dev)
