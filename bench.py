@@ -90,7 +90,37 @@ class ClockSampler:
         self.stop = threading.Event()
         self.t = threading.Thread(target=self._run, daemon=True)
 
+    def _run_nvml(self) -> bool:
+        """NVML in-process (10 ms period): the timed region is ~0.1 s, too short for nvidia-smi."""
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            # CUDA_VISIBLE_DEVICES may renumber devices: resolve through the PCI bus id of the device
+            import torch
+            bus = torch.cuda.get_device_properties(self.index).pci_bus_id
+            dev_id = torch.cuda.get_device_properties(self.index).pci_device_id
+            dom = torch.cuda.get_device_properties(self.index).pci_domain_id
+            h = nv.nvmlDeviceGetHandleByPciBusId(f"{dom:08X}:{bus:02X}:{dev_id:02X}.0")
+            mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            bits = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "hw_thermal_slowdown": 0x40,
+                    "sw_thermal_slowdown": 0x20}
+            while not self.stop.is_set():
+                sm = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+                rs = nv.nvmlDeviceGetCurrentClocksEventReasons(h) if hasattr(
+                    nv, "nvmlDeviceGetCurrentClocksEventReasons") else nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                pw = nv.nvmlDeviceGetPowerUsage(h) / 1000.0
+                row = [str(self.index), str(sm), str(mx), str(pw)]
+                for name in ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"):
+                    row.append("Active" if (rs & bits[name]) else "Not Active")
+                self.rows.append(row)
+                self.stop.wait(0.01)
+            return True
+        except Exception:
+            return False
+
     def _run(self):
+        if self._run_nvml():
+            return
         while not self.stop.is_set():
             try:
                 out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
