@@ -41,8 +41,8 @@ def parse():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--scans", type=int, default=1024, help="sensor poses per GPU per step")
     ap.add_argument("--e2e-scans", type=int, default=1024, help="sensor poses per e2e step")
-    ap.add_argument("--ref-scans", type=int, default=4, help="scans per step of the CPU arm")
-    ap.add_argument("--cpu-baseline-scans", type=int, default=24)
+    ap.add_argument("--ref-scans", type=int, default=24, help="scans per step of the CPU arm (~1-2 s/step)")
+    ap.add_argument("--cpu-baseline-scans", type=int, default=192, help="~10-20 s of CPU work")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-secondary", action="store_true")
     ap.add_argument("--gather", action="store_true", help="also time an NCCL all-gather of results")
@@ -489,7 +489,7 @@ def run_b200(args):
                 "bvh_nodes": st["bvh_nodes"], "mesh_nodes": st["mesh_nodes"],
             },
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": traffic, "kernel": "cast_kernel<LIDAR>",
+                         "frac": achieved / peak, "traffic": traffic, "kernel": "cast_kernel<LIDAR> (+ its mesh-pair kernels: one b2_lidar_cast_device)",
                          "kernel_ms": ms_kernel, "algorithmic_bytes_per_launch": alg_bytes,
                          "peak_source": how,
                          "note": "ray casting is traversal/FP64-issue bound, not HBM bound (SURVEY.md M3)"},

@@ -182,6 +182,10 @@ int b2_camera_render_to_cloud(b2_camera* cam, int32_t ncam, const int32_t* cam_w
                               const double* cam_pos, const double* cam_mat, float* gl_depth,
                               float* depth32fc1, void* cloud);
 
+/* N2: RGB8 row flip of ncam images of this camera model (ref:src/mujoco_cameras.cpp:243-249) for
+ * colour buffers that already live on the device (e.g. CUDA-GL interop).  [ncam*H*W*3] bytes. */
+int b2_rgb_flip_device(b2_camera* cam, int32_t ncam, const uint8_t* d_rgb_gl, uint8_t* d_rgb_out);
+
 /* ---- introspection used by bench.py / tests ------------------------------------------------ */
 /* number of kernels this library has launched in this process (all scenes / cameras) */
 long long b2_launch_count(void);

@@ -76,6 +76,7 @@ SYMBOLS = {
     "b2_camera_render_depth_device": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p,
                                                 C.c_void_p, C.c_void_p]),
     "b2_camera_render_to_cloud": (C.c_int, [C.c_void_p, C.c_int32] + [C.c_void_p] * 6),
+    "b2_rgb_flip_device": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
 }
 
 _lib = None

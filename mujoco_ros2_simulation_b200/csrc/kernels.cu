@@ -204,4 +204,49 @@ cudaError_t launch_depth_to_cloud(const DepthParams& p, cudaStream_t stream) {
   return cudaGetLastError();
 }
 
+// =============================================================================================
+// N2: RGB8 row flip (ref:src/mujoco_cameras.cpp:243-249): GL rows are bottom-up, Image rows are
+// top-down.  Pure copy, 6 B/pixel; 16-B vectors when a row is a multiple of 16 B.
+// =============================================================================================
+__global__ void __launch_bounds__(256) rgb_flip_kernel(const uint8_t* __restrict__ in,
+                                                       uint8_t* __restrict__ out, int ncam,
+                                                       int row_bytes, int height, int vec16) {
+  const long long per_cam = (long long)row_bytes * height;
+  if (vec16) {
+    const int row_v = row_bytes >> 4;
+    const long long total = (long long)ncam * height * row_v;
+    const uint4* src = reinterpret_cast<const uint4*>(in);
+    uint4* dst = reinterpret_cast<uint4*>(out);
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+      const long long cam = i / ((long long)height * row_v);
+      const long long rem = i - cam * (long long)height * row_v;
+      const int h = (int)(rem / row_v), x = (int)(rem - (long long)h * row_v);
+      dst[cam * (per_cam >> 4) + (long long)(height - 1 - h) * row_v + x] = __ldcs(src + i);
+    }
+  } else {
+    const long long total = (long long)ncam * per_cam;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+      const long long cam = i / per_cam;
+      const long long rem = i - cam * per_cam;
+      const int h = (int)(rem / row_bytes), x = (int)(rem - (long long)h * row_bytes);
+      out[cam * per_cam + (long long)(height - 1 - h) * row_bytes + x] = in[i];
+    }
+  }
+}
+
+cudaError_t launch_rgb_flip(const uint8_t* in, uint8_t* out, int ncam, int width, int height,
+                            cudaStream_t stream) {
+  const int row_bytes = width * 3;
+  const long long bytes = (long long)ncam * row_bytes * height;
+  if (bytes <= 0) return cudaSuccess;
+  const int vec16 = (row_bytes % 16 == 0) && (((uintptr_t)in & 15) == 0) && (((uintptr_t)out & 15) == 0);
+  const long long work = vec16 ? bytes / 16 : bytes;
+  long long blocks = (work + 255) / 256;
+  if (blocks > 148 * 32) blocks = 148 * 32;
+  rgb_flip_kernel<<<(unsigned)blocks, 256, 0, stream>>>(in, out, ncam, row_bytes, height, vec16);
+  return cudaGetLastError();
+}
+
 }  // namespace b2

@@ -49,5 +49,9 @@ size_t cast_stage_bytes(int nslot, int nwnode, int ngeom);  // shared memory of 
 // K3: depth linearise + flip + PointCloud2 projection.
 cudaError_t launch_depth_to_cloud(const DepthParams& p, cudaStream_t stream);
 
+// N2: RGB8 row flip of ncam images (GL bottom-up -> Image top-down).
+cudaError_t launch_rgb_flip(const uint8_t* in, uint8_t* out, int ncam, int width, int height,
+                            cudaStream_t stream);
+
 }  // namespace b2
 #endif

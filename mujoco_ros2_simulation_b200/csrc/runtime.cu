@@ -998,6 +998,17 @@ int b2_camera_render_depth_device(b2_camera* c, int32_t ncam, const int32_t* d_c
   return run_cast(s, p, c->stream);
 }
 
+int b2_rgb_flip_device(b2_camera* c, int32_t ncam, const uint8_t* d_rgb_gl, uint8_t* d_rgb_out) {
+  if (!c) return fail(B2_ERR_INVALID, "null camera");
+  if (ncam < 0) return fail(B2_ERR_INVALID, "negative ncam");
+  if (ncam == 0) return B2_OK;
+  if (!d_rgb_gl || !d_rgb_out) return fail(B2_ERR_INVALID, "null image buffer");
+  B2_CUDA(cudaSetDevice(c->device));
+  B2_CUDA(launch_rgb_flip(d_rgb_gl, d_rgb_out, ncam, c->desc.width, c->desc.height, c->stream));
+  g_launches++;
+  return B2_OK;
+}
+
 int b2_camera_render_to_cloud(b2_camera* c, int32_t ncam, const int32_t* cam_world,
                               const double* cam_pos, const double* cam_mat, float* gl_depth,
                               float* depth32fc1, void* cloud) {

@@ -234,6 +234,10 @@ class DepthCamera:
         _capi.check(self.lib.b2_depth_to_cloud_device(self._h, int(ncam), _ptr(d_gl_depth),
                                                       _ptr(d_depth), _ptr(d_cloud)))
 
+    def rgb_flip_device(self, ncam, d_rgb_gl, d_rgb_out):
+        """uint8 CUDA tensors [ncam,H,W,3]: GL bottom-up rows -> Image top-down rows."""
+        _capi.check(self.lib.b2_rgb_flip_device(self._h, int(ncam), _ptr(d_rgb_gl), _ptr(d_rgb_out)))
+
     def render_depth_device(self, ncam, d_pos, d_mat, d_gl_depth, d_world=None):
         _capi.check(self.lib.b2_camera_render_depth_device(self._h, int(ncam), _ptr(d_world),
                                                            _ptr(d_pos), _ptr(d_mat),

@@ -1,0 +1,141 @@
+"""GPU tier: edge cases of the ray path against the oracle (bit-exact), and the small N2 kernel."""
+import numpy as np
+import pytest
+
+from mujoco_ros2_simulation_b200 import engine, scenes
+from mujoco_ros2_simulation_b200.model import (GEOM_BOX, GEOM_CAPSULE, GEOM_CYLINDER, GEOM_ELLIPSOID,
+                                               GEOM_PLANE, GEOM_SPHERE, Model, Poses, random_rotations)
+
+pytestmark = pytest.mark.gpu
+EYE = np.eye(3).reshape(9)
+
+
+def _check(oracle, model, poses, pnt, vec, **kw):
+    s = engine.Scene(model)
+    s.update_poses(poses)
+    d2, g2 = s.multiray(pnt, vec, **kw)
+    o = oracle.OracleScene(model, poses)
+    d, g = o.multi_ray(pnt, vec, nthread=4, **kw)
+    assert np.array_equal(g, g2), np.nonzero(g != g2)[0][:5]
+    assert np.array_equal(d, d2)
+    s.close()
+    return d, g
+
+
+def _prims(rng, n, types, centre_scale=5.0, offset=0.0):
+    t = rng.choice(types, size=n)
+    size = rng.uniform(0.1, 1.0, size=(n, 3))
+    pos = rng.normal(size=(n, 3)) * centre_scale + offset
+    mat = random_rotations(rng, n).reshape(n, 9)
+    m = Model(t, np.zeros(n, int), np.zeros(n, int), -np.ones(n, int), -np.ones(n, int), size,
+              np.ones((n, 4)), np.zeros((0, 4)), [0])
+    return m, Poses(pos, mat)
+
+
+def test_origin_inside_geoms(oracle):
+    """rays that START inside primitives hit the far wall (ray_quad's second root, box exit face)"""
+    rng = np.random.default_rng(21)
+    types = [GEOM_SPHERE, GEOM_CAPSULE, GEOM_ELLIPSOID, GEOM_CYLINDER, GEOM_BOX]
+    m, P = _prims(rng, 40, types, centre_scale=3.0)
+    for g in (0, 7, 19, 33):
+        pnt = P.geom_xpos[0, g] + rng.normal(size=3) * 0.02      # well inside geom g
+        vec = rng.normal(size=(512, 3))
+        d, gid = _check(oracle, m, P, pnt, vec)
+        assert (gid >= 0).all() and (d > 0).all()
+
+
+def test_far_from_world_origin(oracle):
+    """coordinates around 1e4 m: the fp32 culling must stay conservative (origin slack, box pad)"""
+    rng = np.random.default_rng(22)
+    m, P = _prims(rng, 120, [GEOM_SPHERE, GEOM_BOX, GEOM_CAPSULE, GEOM_CYLINDER, GEOM_ELLIPSOID],
+                  centre_scale=8.0, offset=np.array([1.0e4, -2.0e4, 3.0e3]))
+    pnt = np.array([1.0e4, -2.0e4, 3.0e3]) + np.array([0.3, -0.2, 0.1])
+    el = rng.uniform(-0.5, 0.5, 4096)
+    az = np.sort(rng.uniform(-np.pi, np.pi, 4096))
+    vec = np.stack([np.cos(el) * np.cos(az), np.cos(el) * np.sin(az), np.sin(el)], 1)
+    d, g = _check(oracle, m, P, pnt, vec)
+    assert (g >= 0).mean() > 0.05
+
+
+def test_tiny_and_huge_geoms_and_nonunit_rays(oracle):
+    rng = np.random.default_rng(23)
+    m, P = _prims(rng, 60, [GEOM_SPHERE, GEOM_BOX, GEOM_CYLINDER], centre_scale=4.0)
+    m.geom_size[:10] *= 1e-3         # millimetre geoms
+    m.geom_size[10:14] *= 30.0       # geoms that swallow the origin
+    vec = rng.normal(size=(2048, 3)) * 10 ** rng.uniform(-3, 3, size=(2048, 1))
+    _check(oracle, m, P, np.array([0.1, 0.2, -0.1]), vec)
+
+
+def test_planes_finite_tilted_and_many(oracle):
+    """several planes (kept outside the BVH), finite and tilted, one-sided test"""
+    rng = np.random.default_rng(24)
+    n = 6
+    R = random_rotations(rng, n).reshape(n, 9)
+    R[0] = EYE
+    size = np.array([[0, 0, .01], [2, 3, .01], [0, 1.5, .01], [4, 0, .01], [1, 1, .01], [0, 0, .01]], float)
+    pos = rng.normal(size=(n, 3)) * 2
+    pos[0] = (0, 0, -1.0)
+    m = Model([GEOM_PLANE] * n, np.zeros(n, int), np.zeros(n, int), -np.ones(n, int), -np.ones(n, int),
+              size, np.ones((n, 4)), np.zeros((0, 4)), [0])
+    vec = rng.normal(size=(4096, 3))
+    d, g = _check(oracle, m, Poses(pos, R), np.array([0.2, -0.1, 0.5]), vec)
+    assert len(set(g.tolist())) >= 4
+
+
+def test_incoherent_rays_and_overflowing_candidates(oracle):
+    """random directions (cone test disabled per group) on a dense cluster of overlapping boxes:
+    more candidates than the per-group list holds -> drained in several passes"""
+    rng = np.random.default_rng(25)
+    n = 400
+    m, P = _prims(rng, n, [GEOM_BOX, GEOM_SPHERE], centre_scale=0.6)
+    m.geom_size[:] = rng.uniform(0.5, 1.5, size=(n, 3))        # everything overlaps everything
+    vec = rng.normal(size=(1024, 3))
+    _check(oracle, m, P, np.array([6.0, 0.5, 0.2]), vec)
+    _check(oracle, m, P, np.array([6.0, 0.5, 0.2]), vec, cutoff=5.0)
+    # coherent fan through the same cluster
+    az = np.linspace(np.pi - 0.4, np.pi + 0.4, 2048)
+    fan = np.stack([np.cos(az), np.sin(az), 0 * az], 1)
+    _check(oracle, m, P, np.array([6.0, 0.5, 0.2]), fan)
+
+
+def test_mesh_heavy_scene_in_place_and_split_paths(oracle):
+    """only mesh geoms, overlapping: small launch (in-place mesh tracing) and large launch (pair
+    kernels, many pairs per ray, ties between coincident mesh instances) agree with the oracle"""
+    cs = scenes.clutter500(n_el=16, n_az=128)
+    m = cs.model
+    keep = np.nonzero(m.geom_type == 7)[0][:40]
+    n = len(keep) + 10
+    dup = np.concatenate([keep, keep[:10]])                     # coincident copies -> geomid ties
+    model = Model(m.geom_type[dup], np.zeros(n, int), np.zeros(n, int), -np.ones(n, int), m.geom_dataid[dup],
+                  m.geom_size[dup], np.ones((n, 4)), np.zeros((0, 4)), [0], m.mesh_vertadr, m.mesh_vertnum,
+                  m.mesh_faceadr, m.mesh_facenum, m.mesh_vert, m.mesh_face)
+    rng = np.random.default_rng(26)
+    pos = rng.uniform(-2.5, 2.5, size=(n, 3))
+    pos[len(keep):] = pos[:10]
+    mat = random_rotations(rng, n).reshape(n, 9)
+    mat[len(keep):] = mat[:10]
+    P = Poses(pos, mat)
+    pnt = np.array([7.0, 0.0, 0.0])
+    az = np.linspace(np.pi - 0.5, np.pi + 0.5, 400)
+    el = np.linspace(-0.4, 0.4, 200)
+    A, E = np.meshgrid(az, el)
+    vec = np.stack([np.cos(E) * np.cos(A), np.cos(E) * np.sin(A), np.sin(E)], -1).reshape(-1, 3)
+    d_small, g_small = _check(oracle, model, P, pnt, vec[:4000])     # < 65536 rays: in-place path
+    d_big, g_big = _check(oracle, model, P, pnt, vec)                # 80000 rays: split path
+    assert np.array_equal(d_big[:4000], d_small) and np.array_equal(g_big[:4000], g_small)
+    assert (g_big >= 0).mean() > 0.3
+    hit = g_big[g_big >= 0]
+    assert hit.max() < len(keep)          # a coincident copy (higher id) never wins a tie
+
+
+def test_rgb_flip_kernel():
+    import torch
+    dev = torch.device("cuda", 0)
+    for (w, h) in ((640, 480), (322, 7)):
+        cam = engine.DepthCamera(scenes.CameraSpec(w, h, 58.0))
+        gen = torch.Generator(device=dev).manual_seed(3)
+        rgb = torch.randint(0, 256, (3, h, w, 3), dtype=torch.uint8, device=dev, generator=gen)
+        out = torch.empty_like(rgb)
+        cam.rgb_flip_device(3, rgb, out)
+        torch.cuda.synchronize()
+        assert torch.equal(out, rgb.flip(1))
