@@ -338,6 +338,11 @@ __global__ void __launch_bounds__(kMeshThreads, B2_MESH_MINBLOCKS)
           stack[sp] = first0 ? n.c1 : n.c0;
           stack_t[sp] = first0 ? t1 : t0;
           sp++;
+#ifdef B2_MESH_PREFETCH
+          // the postponed child will be popped later: start its fetch now (inner nodes only)
+          if (stack[sp - 1] >= 0)
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(nodes + stack[sp - 1]));
+#endif
         }
         cur = first0 ? n.c0 : n.c1;
       } else if (h0) {

@@ -7,6 +7,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <mutex>
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
@@ -123,6 +124,9 @@ struct b2_scene {
   DevBuf<uint32_t> d_aff_ray;
   DevBuf<unsigned long long> d_aff_bits, d_aff_prim;
   bool has_mesh_geoms = false;
+  // The plugin's physics, lidar and camera threads share one scene: every enqueue on the scene's
+  // stream (and every use of the scene-owned scratch) is serialised by this mutex.
+  std::recursive_mutex mtx;
   // scratch for b2_multiray
   DevBuf<double> d_mr_vec, d_mr_dist, d_mr_pnt;
   DevBuf<int32_t> d_mr_id;
@@ -279,6 +283,7 @@ void cast_shape(const b2_scene* s, const CastParams& p, bool& stage, int& tiles_
 // chunk runs K2 -> K2b -> K2c -> K2d (+ the overflow clean-up guard).
 int run_cast(b2_scene* s, CastParams p, cudaStream_t stream) {
   if (p.nscan <= 0 || p.nray <= 0) return B2_OK;
+  std::lock_guard<std::recursive_mutex> lock(s->mtx);
   const long long total = (long long)p.nscan * p.nray;
   bool split = s->has_mesh_geoms && total >= 65536;
   const int force = env_int("B2_SPLIT", -1);
@@ -522,6 +527,7 @@ static int update_poses_common(b2_scene* s, int32_t world0, int32_t nworld, cons
   if (!xpos || !xmat) return fail(B2_ERR_INVALID, "null pose array");
   if (world0 < 0 || nworld < 1 || world0 + nworld > s->nworld)
     return fail(B2_ERR_INVALID, "world range out of bounds");
+  std::lock_guard<std::recursive_mutex> lock(s->mtx);
   B2_CUDA(cudaSetDevice(s->device));
   if (s->ngeom == 0) return B2_OK;
   const size_t G = (size_t)s->ngeom;
@@ -577,6 +583,7 @@ int b2_scene_rebuild(b2_scene* s, int32_t world) {
   if (!s) return fail(B2_ERR_INVALID, "null scene");
   if (world < 0 || world >= s->nworld) return fail(B2_ERR_INVALID, "world out of range");
   if (!s->topo_built) return fail(B2_ERR_INVALID, "b2_scene_rebuild before any pose update");
+  std::lock_guard<std::recursive_mutex> lock(s->mtx);
   B2_CUDA(cudaSetDevice(s->device));
   if (s->ngeom == 0) return B2_OK;
   const size_t G = (size_t)s->ngeom;
@@ -780,6 +787,7 @@ int b2_multiray(b2_scene* s, int32_t world, const double pnt[3], const double* v
   if (world < 0 || world >= s->nworld) return fail(B2_ERR_INVALID, "world out of range");
   if (s->ngeom > 0 && !s->topo_built)
     return fail(B2_ERR_INVALID, "b2_multiray before the first b2_scene_update_poses");
+  std::lock_guard<std::recursive_mutex> lock(s->mtx);  // scene-owned scratch until the sync below
   B2_CUDA(cudaSetDevice(s->device));
   std::vector<uint8_t> elim;
   eliminate_flags(s->hm, geomgroup, flg_static, bodyexclude, elim);
