@@ -139,3 +139,63 @@ def test_rgb_flip_kernel():
         cam.rgb_flip_device(3, rgb, out)
         torch.cuda.synchronize()
         assert torch.equal(out, rgb.flip(1))
+
+
+def test_large_scene_unstaged_bvh_and_deep_tree(oracle, emu):
+    """6000 geoms: the geom BVH (3 levels of fanout-32 nodes, ~200 KB) no longer fits the per-CTA
+    shared-memory stage, so the cast reads it through the read-only path; several lidars share
+    one scene."""
+    rng = np.random.default_rng(31)
+    n = 6000
+    m, P = _prims(rng, n, [GEOM_SPHERE, GEOM_BOX, GEOM_CAPSULE, GEOM_CYLINDER, GEOM_ELLIPSOID],
+                  centre_scale=25.0)
+    m.geom_size[:] *= 0.6
+    st = emu.bvh_stats(m, P)
+    assert st["depth"] >= 3 and st["bvh_slots"] * 32 > 96 * 1024
+    s = engine.Scene(m)
+    s.update_poses(P)
+    o = oracle.OracleScene(m, P)
+    specs = [scenes.LidarSpec(scenes.spinning_lidar_dirs(8, 512), tile_w=512),
+             scenes.LidarSpec(scenes.planar_lidar_dirs(0.0, 2 * np.pi / 1000, 1000), range_min=0.5, range_max=40.0),
+             scenes.LidarSpec(scenes.spinning_lidar_dirs(4, 64), tile_w=64, geomgroup=[1, 0, 0, 0, 0, 0])]
+    lids = [engine.Lidar(s, sp) for sp in specs]
+    pos = np.array([[0.5, -0.3, 0.2], [10.0, 5.0, -3.0]])
+    mat = np.stack([EYE, random_rotations(rng, 1)[0].reshape(9)])
+    for sp, lid in zip(specs, lids):
+        out = lid.cast(pos, mat, want=("ranges", "geomid", "dist"))
+        for i in range(2):
+            r, g, raw = o.lidar_scan(sp, pos[i], mat[i], nthread=8)
+            assert np.array_equal(out["geomid"][i], g)
+            assert np.array_equal(out["dist"][i], raw) and np.array_equal(out["ranges"][i], r)
+    assert (out["geomid"] >= 0).any()
+
+
+def test_two_threads_share_one_scene(oracle):
+    """the plugin's lidar and camera threads call into the same scene concurrently"""
+    import threading
+    cs = scenes.clutter500(n_el=16, n_az=128)
+    s = engine.Scene(cs.model)
+    s.update_poses(cs.poses)
+    lid_a = engine.Lidar(s, cs.lidar)
+    lid_b = engine.Lidar(s, scenes.LidarSpec(cs.lidar.local_dir[::3], bodyexclude=63))
+    pos, mat = cs.sensor_poses(40)     # 40 x 2048 rays: the split mesh path with shared scratch
+    ref_a = lid_a.cast(pos, mat, want=("geomid", "dist"))
+    ref_b = lid_b.cast(pos, mat, want=("geomid", "dist"))
+    errs = []
+
+    def work(lid, ref):
+        try:
+            for _ in range(6):
+                out = lid.cast(pos, mat, want=("geomid", "dist"))
+                assert np.array_equal(out["dist"], ref["dist"]) and np.array_equal(out["geomid"], ref["geomid"])
+                s.update_poses(cs.poses)
+        except Exception as e:  # noqa: BLE001
+            errs.append(e)
+
+    ts = [threading.Thread(target=work, args=(lid_a, ref_a)), threading.Thread(target=work, args=(lid_b, ref_b))]
+    [t.start() for t in ts]
+    [t.join() for t in ts]
+    assert not errs, errs
+    o = oracle.OracleScene(cs.model, cs.poses)
+    r, g, raw = o.lidar_scan(cs.lidar, pos[3], mat[3], nthread=8)
+    assert np.array_equal(ref_a["dist"][3], raw) and np.array_equal(ref_a["geomid"][3], g)
