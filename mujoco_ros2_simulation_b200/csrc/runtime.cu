@@ -675,9 +675,11 @@ int b2_lidar_destroy(b2_lidar* l) {
   return B2_OK;
 }
 
-static int lidar_launch(b2_lidar* l, int32_t nscan, const int32_t* d_world, const double* d_pos,
-                        const double* d_mat, float* d_ranges, int32_t* d_geomid, double* d_dist,
-                        float* d_xyz, cudaStream_t stream) {
+// scan0: index of the first of these scans in the caller's batch (scans without a world table map
+// to world (scan0 + s) % nworld)
+static int lidar_launch(b2_lidar* l, int32_t nscan, int32_t scan0, const int32_t* d_world,
+                        const double* d_pos, const double* d_mat, float* d_ranges,
+                        int32_t* d_geomid, double* d_dist, float* d_xyz, cudaStream_t stream) {
   b2_scene* s = l->scene;
   if (nscan == 0 || l->nray == 0) return B2_OK;
   if (s->ngeom > 0 && !s->topo_built)
@@ -693,6 +695,7 @@ static int lidar_launch(b2_lidar* l, int32_t nscan, const int32_t* d_world, cons
   p.range_min = l->range_min;
   p.range_max = l->range_max;
   p.nscan = nscan;
+  p.scan0 = scan0;
   p.scan_world = d_world;
   p.spos = d_pos;
   p.smat = d_mat;
@@ -710,7 +713,7 @@ int b2_lidar_cast_device(b2_lidar* l, int32_t nscan, const int32_t* d_scan_world
   if (nscan < 0) return fail(B2_ERR_INVALID, "negative nscan");
   if (nscan > 0 && (!d_sensor_pos || !d_sensor_mat)) return fail(B2_ERR_INVALID, "null sensor pose");
   B2_CUDA(cudaSetDevice(l->scene->device));
-  return lidar_launch(l, nscan, d_scan_world, d_sensor_pos, d_sensor_mat, d_ranges, d_geomid,
+  return lidar_launch(l, nscan, 0, d_scan_world, d_sensor_pos, d_sensor_mat, d_ranges, d_geomid,
                       d_dist, d_xyz, l->scene->stream);
 }
 
@@ -743,12 +746,24 @@ int b2_lidar_cast(b2_lidar* l, int32_t nscan, const int32_t* scan_world, const d
   int nchunk = env_int("B2_E2E_CHUNKS", 8);
   if (nchunk > nscan) nchunk = nscan;
   if (nchunk < 1) nchunk = 1;
-  for (int c = 0; c < nchunk; c++) {
-    const int s0 = (int)((long long)nscan * c / nchunk), s1 = (int)((long long)nscan * (c + 1) / nchunk);
+  // equal chunks, except that the last one is cut into quarters: the copy of the final piece is
+  // the only one nothing overlaps, so it should be small
+  std::vector<int> bounds;
+  for (int c = 0; c < nchunk; c++) bounds.push_back((int)((long long)nscan * c / nchunk));
+  {
+    const int last0 = bounds.back(), len = nscan - last0;
+    for (int q = 1; q < 4 && nchunk > 1; q++) {
+      const int b = last0 + (int)((long long)len * q / 4);
+      if (b > bounds.back() && b < nscan) bounds.push_back(b);
+    }
+  }
+  bounds.push_back(nscan);
+  for (size_t c = 0; c + 1 < bounds.size(); c++) {
+    const int s0 = bounds[c], s1 = bounds[c + 1];
     const int ns = s1 - s0;
     if (ns <= 0) continue;
     const size_t off = (size_t)s0 * l->nray, cnt = (size_t)ns * l->nray;
-    int rc = lidar_launch(l, ns, scan_world ? l->d_world.ptr + s0 : nullptr, l->d_spos.ptr + 3 * (size_t)s0,
+    int rc = lidar_launch(l, ns, s0, scan_world ? l->d_world.ptr + s0 : nullptr, l->d_spos.ptr + 3 * (size_t)s0,
                           l->d_smat.ptr + 9 * (size_t)s0, ranges ? l->d_ranges.ptr + off : nullptr,
                           geomid ? l->d_geomid.ptr + off : nullptr, dist ? l->d_dist.ptr + off : nullptr,
                           xyz ? l->d_xyz.ptr + 3 * off : nullptr, s->stream);
