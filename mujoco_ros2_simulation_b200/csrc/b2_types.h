@@ -141,6 +141,7 @@ struct CastParams {
   int32_t nscan;
   int32_t scan0;              // index of this launch's first scan in the caller's batch (world mapping)
   const int32_t* scan_world;  // nullable
+  int32_t* work_counter;      // [1] next tile group of a persistent (dynamic) K2 launch; nullable
   const double* spos;         // [nscan*3]
   const double* smat;         // [nscan*9]
   // outputs (nullable)

@@ -150,6 +150,8 @@ __device__ __forceinline__ bool scan_ray(const CastParams& p, int scan, int r, d
 
 struct TileGeom {
   int tiles_per_block, tiles_per_scan, chunks_per_scan, tiles_x;
+  // persistent launch (single-world batches): warps fetch tile groups from p.work_counter
+  int dynamic, groups_per_scan, ngroups;
 };
 
 // ray generator of one group: tile t of the group, this lane's ray.  The sensor frame is
@@ -206,9 +208,10 @@ __global__ void __launch_bounds__(kCastThreads, B2_CAST_MINBLOCKS)
   unsigned char* s_stage = smem_raw + kCastWarps * sizeof(WarpScratch);
 
   const int warp_id = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int scan = blockIdx.x / tg.chunks_per_scan;
-  const int chunk = blockIdx.x - scan * tg.chunks_per_scan;
-  const int world = p.scan_world ? p.scan_world[scan] : (p.scan0 + scan) % p.nworld;
+  // a dynamic launch serves one world only (the launcher checks): stage the world of scan 0
+  const int scan_b = tg.dynamic ? 0 : blockIdx.x / tg.chunks_per_scan;
+  const int chunk = blockIdx.x - scan_b * tg.chunks_per_scan;
+  const int world = p.scan_world ? p.scan_world[scan_b] : (p.scan0 + scan_b) % p.nworld;
 
   // geom BVH of this world: child slots (boxes) + topology, staged in shared memory per CTA
   const WideChild* wslots = p.wslots + (size_t)world * p.nslot;
@@ -236,10 +239,25 @@ __global__ void __launch_bounds__(kCastThreads, B2_CAST_MINBLOCKS)
   const float tcap = (MODE == MODE_MULTIRAY) ? f32_up(p.cutoff) : FLT_MAX;
 
   // each warp walks groups of kGroupTiles consecutive tiles of this CTA's chunk
-  for (int t = warp_id * kGroupTiles; t < tg.tiles_per_block; t += kCastWarps * kGroupTiles) {
-    const int tile0 = chunk * tg.tiles_per_block + t;
-    if (tile0 >= tg.tiles_per_scan) break;  // warp-uniform
-    const int nt = ::min(kGroupTiles, ::min(tg.tiles_per_block - t, tg.tiles_per_scan - tile0));
+  // (static launch) or, in a persistent launch, whatever group the global work counter hands out
+  // next -- no warp waits for the slowest group of its CTA
+  for (int t = warp_id * kGroupTiles;; t += kCastWarps * kGroupTiles) {
+    int scan, tile0, nt;
+    if (tg.dynamic) {
+      int g = 0;
+      if (lane == 0) g = atomicAdd(p.work_counter, 1);
+      g = __shfl_sync(0xffffffffu, g, 0);
+      if (g >= tg.ngroups) break;
+      scan = g / tg.groups_per_scan;
+      tile0 = (g - scan * tg.groups_per_scan) * kGroupTiles;
+      nt = ::min(kGroupTiles, tg.tiles_per_scan - tile0);
+    } else {
+      if (t >= tg.tiles_per_block) break;
+      scan = scan_b;
+      tile0 = chunk * tg.tiles_per_block + t;
+      if (tile0 >= tg.tiles_per_scan) break;  // warp-uniform
+      nt = ::min(kGroupTiles, ::min(tg.tiles_per_block - t, tg.tiles_per_scan - tile0));
+    }
     double o[3];
 #pragma unroll
     for (int k = 0; k < 3; k++) o[k] = __ldg(p.spos + (size_t)scan * 3 + k);
@@ -459,13 +477,26 @@ static cudaError_t launch_cast_mode(const CastParams& p, bool stage, int tiles_p
   if (tiles_per_block < kCastWarps) tiles_per_block = kCastWarps;
   tg.tiles_per_block = tiles_per_block;
   tg.chunks_per_scan = (tg.tiles_per_scan + tiles_per_block - 1) / tiles_per_block;
-  const long long nblocks = (long long)p.nscan * tg.chunks_per_scan;
+  long long nblocks = (long long)p.nscan * tg.chunks_per_scan;
   if (nblocks <= 0) return cudaSuccess;
   if (nblocks > 0x7fffffffLL) return cudaErrorInvalidConfiguration;
+  // persistent launch: one resident wave of CTAs whose warps pull groups from the work counter
+  tg.groups_per_scan = (tg.tiles_per_scan + kGroupTiles - 1) / kGroupTiles;
+  const long long ngroups = (long long)p.nscan * tg.groups_per_scan;
+  const long long resident = (long long)sm_count * B2_CAST_MINBLOCKS;
+  tg.dynamic = p.work_counter != nullptr && stage && p.nworld == 1 && ngroups <= 0x7fffffffLL &&
+               ngroups >= 4 * resident * kCastWarps;
+  tg.ngroups = (int)ngroups;
+  const long long nblocks_static = nblocks;
+  if (tg.dynamic) nblocks = resident;
   size_t smem = kCastWarps * sizeof(WarpScratch);
   if (stage) smem += cast_stage_bytes(p.nslot, p.nwnode, p.ngeom);
   const bool split = p.ms.counters != nullptr;
   cudaError_t err;
+  if (tg.dynamic) {
+    err = cudaMemsetAsync(p.work_counter, 0, sizeof(int32_t), stream);
+    if (err != cudaSuccess) return err;
+  }
   if (!split) {
     err = stage ? launch_tile_kernel(cast_kernel<MODE, true, false, false>, p, tg, (unsigned)nblocks,
                                      smem, stream)
@@ -487,7 +518,10 @@ static cudaError_t launch_cast_mode(const CastParams& p, bool stage, int tiles_p
   mesh_final_kernel<MODE><<<mgrid, kMeshThreads, 0, stream>>>(p);
   err = cudaGetLastError();
   if (err != cudaSuccess) return err;
-  // clean-up: recompute the chunk in place if the pair list overflowed (exits at once otherwise)
+  // clean-up: recompute the chunk in place if the pair list overflowed (exits at once otherwise);
+  // always the static tiling -- it is (almost) never more than an empty launch
+  tg.dynamic = 0;
+  nblocks = nblocks_static;
   err = stage ? launch_tile_kernel(cast_kernel<MODE, true, false, true>, p, tg, (unsigned)nblocks,
                                    smem, stream)
               : launch_tile_kernel(cast_kernel<MODE, false, false, true>, p, tg, (unsigned)nblocks,

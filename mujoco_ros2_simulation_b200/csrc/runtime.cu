@@ -290,6 +290,9 @@ int run_cast(b2_scene* s, CastParams p, cudaStream_t stream) {
   if (force == 0) split = false;
   if (force == 1 && s->has_mesh_geoms) split = true;
   int scans_per_chunk = p.nscan;
+  // counters[0..3]: split mesh path; counters[4]: group cursor of a persistent K2 launch
+  B2_CUDA(s->d_counters.reserve(8));
+  p.work_counter = env_int("B2_DYNAMIC", 1) != 0 ? s->d_counters.ptr + 4 : nullptr;
   if (split) {
     // measured on B200 (profiles/r01_sweeps.txt): 8M rays/chunk 5.0, 32M 5.4, whole launch 5.6
     // Grays/s -- fewer, longer kernels lose less in launch gaps and tails; scratch is 68 B/ray
@@ -306,7 +309,6 @@ int run_cast(b2_scene* s, CastParams p, cudaStream_t stream) {
     B2_CUDA(s->d_aff_prim.reserve(aff_cap));
     B2_CUDA(s->d_aff_prim_id.reserve(aff_cap));
     B2_CUDA(s->d_aff_mesh_id.reserve(aff_cap));
-    B2_CUDA(s->d_counters.reserve(4));
     p.ms.pair_slot = s->d_pair_slot.ptr;
     p.ms.pair_geom = s->d_pair_geom.ptr;
     p.ms.pair_x = s->d_pair_x.ptr;

@@ -1,0 +1,130 @@
+"""GPU tier: the persistent (dynamic group fetch) K2 launch against the static tiling and the
+oracle.  Single-world batches above ~1.2 M rays take the persistent launch (B2_DYNAMIC=0 forces
+the static one); both must give the same bits, with and without the split mesh path, in every
+mode (lidar / multiRay / camera rays)."""
+import os
+
+import numpy as np
+import pytest
+
+from mujoco_ros2_simulation_b200 import engine, scenes
+
+pytestmark = pytest.mark.gpu
+
+
+class _env:
+    def __init__(self, **kw):
+        self.kw = kw
+
+    def __enter__(self):
+        self.old = {k: os.environ.get(k) for k in self.kw}
+        os.environ.update({k: str(v) for k, v in self.kw.items()})
+
+    def __exit__(self, *a):
+        for k, v in self.old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+
+
+def _cast_dev(lid, s, pos, mat, xyz=False):
+    import torch
+    dev = torch.device("cuda", 0)
+    n = pos.shape[0]
+    g = torch.full((n, lid.nray), -7, dtype=torch.int32, device=dev)
+    d = torch.full((n, lid.nray), -7.0, dtype=torch.float64, device=dev)
+    r = torch.full((n, lid.nray), -7.0, dtype=torch.float32, device=dev)
+    x = torch.zeros((n, lid.nray, 3), dtype=torch.float32, device=dev) if xyz else None
+    lid.cast_device(n, torch.from_numpy(pos).to(dev), torch.from_numpy(mat).to(dev), None, geomid=g, dist=d,
+                    ranges=r, xyz=x)
+    s.sync()
+    return g.cpu().numpy(), d.cpu().numpy(), r.cpu().numpy(), None if x is None else x.cpu().numpy()
+
+
+@pytest.mark.parametrize("split", [1, 0])
+def test_lidar_dynamic_equals_static_and_oracle(oracle, split):
+    cs = scenes.clutter500()                       # 64 x 2048 rays per scan
+    s = engine.Scene(cs.model)
+    s.update_poses(cs.poses)
+    lid = engine.Lidar(s, cs.lidar)
+    n = 12 if split else 10                        # 1.57 M / 1.31 M rays: above the persistent threshold
+    pos, mat = cs.sensor_poses(n)
+    with _env(B2_DYNAMIC=1, B2_SPLIT=split):
+        dyn = _cast_dev(lid, s, pos, mat, xyz=True)
+    with _env(B2_DYNAMIC=0, B2_SPLIT=split):
+        sta = _cast_dev(lid, s, pos, mat, xyz=True)
+    for a, b in zip(dyn, sta):
+        assert np.array_equal(a, b, equal_nan=True)
+    assert (dyn[0] != -7).all() and (dyn[1] != -7.0).all()      # every ray was written
+    o = oracle.OracleScene(cs.model, cs.poses)
+    for sc in (0, n - 1):
+        r, g, raw = o.lidar_scan(cs.lidar, pos[sc], mat[sc], nthread=8)
+        assert np.array_equal(raw, dyn[1][sc]) and np.array_equal(g, dyn[0][sc])
+        assert np.array_equal(r, dyn[2][sc])
+
+
+def test_ragged_scan_dynamic(oracle):
+    """nray not a multiple of the group (4 tiles x 32 rays) nor of the tile: the last group of every
+    scan is short and its last tile is ragged."""
+    cs = scenes.clutter500(n_el=32, n_az=256)
+    nray = 32 * 256 - 77
+    spec = scenes.LidarSpec(cs.lidar.local_dir[:nray], bodyexclude=63)
+    s = engine.Scene(cs.model)
+    s.update_poses(cs.poses)
+    lid = engine.Lidar(s, spec)
+    pos, mat = cs.sensor_poses(160)                # 1.3 M rays
+    with _env(B2_DYNAMIC=1):
+        dyn = _cast_dev(lid, s, pos, mat)
+    with _env(B2_DYNAMIC=0):
+        sta = _cast_dev(lid, s, pos, mat)
+    for a, b in zip(dyn[:3], sta[:3]):
+        assert np.array_equal(a, b, equal_nan=True)
+    assert (dyn[0] != -7).all()
+    o = oracle.OracleScene(cs.model, cs.poses)
+    r, g, raw = o.lidar_scan(spec, pos[159], mat[159], nthread=8)
+    assert np.array_equal(raw, dyn[1][159]) and np.array_equal(g, dyn[0][159])
+
+
+def test_multiray_dynamic(oracle):
+    cs = scenes.clutter500(n_el=32, n_az=256)
+    s = engine.Scene(cs.model)
+    s.update_poses(cs.poses)
+    rng = np.random.default_rng(11)
+    n = 1_400_000
+    vec = rng.normal(size=(n, 3))
+    pnt = cs.sensor_pos
+    with _env(B2_DYNAMIC=1):
+        d1, g1 = s.multiray(pnt, vec, bodyexclude=63)
+    with _env(B2_DYNAMIC=0):
+        d0, g0 = s.multiray(pnt, vec, bodyexclude=63)
+    assert np.array_equal(d1, d0) and np.array_equal(g1, g0)
+    o = oracle.OracleScene(cs.model, cs.poses)
+    sel = rng.choice(n, 4000, replace=False)
+    d, g = o.multi_ray(pnt, vec[sel], bodyexclude=63, nthread=8)
+    assert np.array_equal(d, d1[sel]) and np.array_equal(g, g1[sel])
+
+
+def test_camera_rays_dynamic():
+    """camera mode (N1): 6 cameras x 640x480 = 1.8 M rays in one world -- persistent == static."""
+    import torch
+    cs = scenes.clutter500(n_el=32, n_az=256)
+    s = engine.Scene(cs.model)
+    s.update_poses(cs.poses)
+    cam = engine.DepthCamera(scenes.CameraSpec(640, 480, 58.0, 0.01, 50.0, 1.0, 12), scene=s)
+    dev = torch.device("cuda", 0)
+    R = np.array([[0, 0, -1.0], [-1.0, 0, 0], [0, 1.0, 0]])
+    n = 6
+    pos = np.array([[3.0 + 0.3 * i, 0.2 * i, 1.5] for i in range(n)])
+    d_pos = torch.from_numpy(pos).to(dev)
+    d_mat = torch.from_numpy(np.tile(R.reshape(1, 9), (n, 1))).to(dev)
+    outs = []
+    for dyn in (1, 0):
+        gl = torch.full((n, 480, 640), -1.0, dtype=torch.float32, device=dev)
+        with _env(B2_DYNAMIC=dyn):
+            cam.render_depth_device(n, d_pos, d_mat, gl)
+        s.sync()
+        outs.append(gl.cpu().numpy())
+    assert np.array_equal(outs[0], outs[1])
+    assert (outs[0] >= 0).all() and (outs[0] < 1.0).mean() > 0.2
+    assert not np.array_equal(outs[0][0], outs[0][5])
