@@ -263,7 +263,61 @@ def other_configs(engine, scenes, torch, dev, stream, nworld3=4096, nworld4=1024
         cam.close()
     lid.close()
     sc.close()
+    out["cfg5_clutter_worlds"] = cfg5(engine, scenes, torch, dev, stream)
     return out
+
+
+def cfg5(engine, scenes, torch, dev, stream, nworld=256):
+    """BASELINE.json configs[4] per-GPU shape at a bounded world count: `nworld` worlds of the
+    clutter500 topology (per-world body jitter, one shared BVH topology, refit every step), each with
+    the 64x2048 lidar and a 640x480 depth camera whose GL depth buffer is ray-cast from the same
+    scene mirror (N1), then linearised + projected (K3).  4096 worlds/GPU is the full size."""
+    cs = scenes.clutter500()
+    P = scenes.clutter_worlds(cs, nworld)
+    sc = engine.Scene(cs.model, nworld=nworld, device=dev.index, stream=stream.cuda_stream)
+    lid = engine.Lidar(sc, cs.lidar)
+    cam = engine.DepthCamera(scenes.depth_camera(), scene=sc, device=dev.index)
+    pos, mat = cs.sensor_poses(nworld)
+    R = np.array([[0, 0, -1.0], [-1.0, 0, 0], [0, 1.0, 0]]).reshape(1, 9)
+    with torch.cuda.stream(stream):
+        xpos, xmat = torch.from_numpy(P.geom_xpos).to(dev), torch.from_numpy(P.geom_xmat).to(dev)
+        spos, smat = torch.from_numpy(pos).to(dev), torch.from_numpy(mat).to(dev)
+        sw = torch.arange(nworld, dtype=torch.int32, device=dev)
+        cpos = torch.from_numpy(np.tile([[3.0, 0.0, 1.5]], (nworld, 1))).to(dev)
+        cmat = torch.from_numpy(np.tile(R, (nworld, 1))).to(dev)
+        rng = torch.empty((nworld, lid.nray), dtype=torch.float32, device=dev)
+        gid = torch.empty((nworld, lid.nray), dtype=torch.int32, device=dev)
+        gl = torch.empty((nworld, 480, 640), dtype=torch.float32, device=dev)
+        dimg = torch.empty_like(gl)
+        cloud = torch.empty((nworld, 480, 640, 3), dtype=torch.float32, device=dev)
+        a, b, c = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+
+        def step():
+            sc.update_poses_device(xpos, xmat)
+            lid.cast_device(nworld, spos, smat, sw, ranges=rng, geomid=gid)
+            b.record(stream)
+            cam.render_depth_device(nworld, cpos, cmat, gl, d_world=sw)
+            cam.depth_to_cloud_device(nworld, gl, dimg, cloud)
+
+        for _ in range(2):
+            step()
+        reps, ms_l, ms_c = 3, 0.0, 0.0
+        for _ in range(reps):
+            a.record(stream)
+            step()
+            c.record(stream)
+            stream.synchronize()
+            ms_l += a.elapsed_time(b) / reps
+            ms_c += b.elapsed_time(c) / reps
+        res = {"workload": f"{nworld} worlds (of 4096/GPU) x (64x2048 lidar + 640x480 ray-cast depth -> 32FC1 + "
+                           "cloud) on the clutter500 topology, poses refit per step",
+               "lidar_grays_per_s": nworld * lid.nray / (ms_l * 1e-3) / 1e9, "lidar_ms": ms_l,
+               "camera_grays_per_s": nworld * 480 * 640 / (ms_c * 1e-3) / 1e9, "camera_ms": ms_c,
+               "hit_fraction": float((gid >= 0).float().mean().item())}
+    cam.close()
+    lid.close()
+    sc.close()
+    return res
 
 
 def run_b200(args):

@@ -278,7 +278,9 @@ __global__ void __launch_bounds__(kCastThreads, B2_CAST_MINBLOCKS)
 // code runs with most lanes active instead of whenever a single lane happens to hit a leaf.
 // The pair already passed mj_rayMesh's box pre-test in K2, so no post-test is needed here.
 #ifndef B2_MESH_MINBLOCKS
-#define B2_MESH_MINBLOCKS 5  // 4 / 5 / 6 measured: 5.44 / 5.50 / 5.47 Grays/s at the time
+// CTAs/SM (register cap): 4 / 5 / 6 measured 5.44 / 5.50 / 5.47 Grays/s early on; later, with the
+// kernel bound by node-fetch latency, 5 / 6 / 8 / 10 gave 6.57 / 6.52 / 6.64 / 6.57 (64 regs, 32 warps)
+#define B2_MESH_MINBLOCKS 8
 #endif
 #ifndef B2_MESH_REFILL
 #define B2_MESH_REFILL 16  // idle lanes per warp that trigger a refill (2..16 measured: 16 best)
