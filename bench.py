@@ -67,6 +67,44 @@ def env_rank():
             int(os.environ.get("WORLD_SIZE", 1)))
 
 
+class NumaNear:
+    """Run the enclosed block on the CPUs of the NUMA node the GPU hangs off, so that pinned host
+    buffers allocated inside it are first-touched on that node (with 8 ranks on a 2-socket host
+    the D2H streams otherwise cross the socket link).  Restores the affinity on exit; does nothing
+    when the topology cannot be read."""
+
+    def __init__(self, index: int):
+        self.index, self.node, self.old = index, None, None
+
+    def __enter__(self):
+        try:
+            import torch
+            p = torch.cuda.get_device_properties(self.index)
+            bdf = f"{p.pci_domain_id:04x}:{p.pci_bus_id:02x}:{p.pci_device_id:02x}.0"
+            node = int(open(f"/sys/bus/pci/devices/{bdf}/numa_node").read())
+            if node < 0:
+                return self
+            cpus = set()
+            for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+                lo, _, hi = part.partition("-")
+                cpus.update(range(int(lo), int(hi or lo) + 1))
+            self.old = os.sched_getaffinity(0)
+            cpus &= self.old
+            if cpus:
+                os.sched_setaffinity(0, cpus)
+                self.node = node
+        except Exception:
+            pass
+        return self
+
+    def __exit__(self, *a):
+        if self.old is not None and self.node is not None:
+            try:
+                os.sched_setaffinity(0, self.old)
+            except Exception:
+                pass
+
+
 def measured_peak():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -413,13 +451,16 @@ def run_b200(args):
 
     # ---- e2e: host buffers through the blocking C-ABI call, copies inside the timed region ------
     es = min(args.e2e_scans, nscan)
-    h_pos = torch.from_numpy(pos[:es].copy()).pin_memory()
-    h_mat = torch.from_numpy(mat[:es].copy()).pin_memory()
-    h_world = torch.zeros(es, dtype=torch.int32).pin_memory()
-    h_ranges = torch.empty((es, nray), dtype=torch.float32).pin_memory()
-    h_geomid = torch.empty((es, nray), dtype=torch.int32).pin_memory()
-    h_xpos = torch.from_numpy(cs.poses.geom_xpos.copy()).pin_memory()
-    h_xmat = torch.from_numpy(cs.poses.geom_xmat.copy()).pin_memory()
+    with NumaNear(local_rank) as near:  # pinned buffers on the GPU's own NUMA node
+        h_pos = torch.from_numpy(pos[:es].copy()).pin_memory()
+        h_mat = torch.from_numpy(mat[:es].copy()).pin_memory()
+        h_world = torch.zeros(es, dtype=torch.int32).pin_memory()
+        h_ranges = torch.empty((es, nray), dtype=torch.float32).pin_memory()
+        h_geomid = torch.empty((es, nray), dtype=torch.int32).pin_memory()
+        h_xpos = torch.from_numpy(cs.poses.geom_xpos.copy()).pin_memory()
+        h_xmat = torch.from_numpy(cs.poses.geom_xmat.copy()).pin_memory()
+        h_ranges.zero_()
+        h_geomid.zero_()
     lib = scene.lib
 
     def e2e_step():
@@ -549,7 +590,7 @@ def run_b200(args):
                          "note": "ray casting is traversal/FP64-issue bound, not HBM bound (SURVEY.md M3)"},
             "cpu_baseline": cpu,
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "scans_per_step": es},
+                    "scans_per_step": es, "pinned_numa_node": near.node},
             "gpu_launches": int(launches),
             "clocks": clk.summary(),
             "secondary": secondary,

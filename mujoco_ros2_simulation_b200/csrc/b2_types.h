@@ -48,6 +48,19 @@ struct B2_ALIGN(16) BvhNode {
 };
 static_assert(sizeof(BvhNode) == 64, "BvhNode must be 64 B");
 
+// The per-mesh triangle BVHs are collapsed to fanout 4 (bvh_build.cpp collapse4): half as many
+// dependent node fetches per ray as the BVH2 -- the mesh kernels are bound by exactly that latency.
+// Boxes are stored per axis for the four children (seven 16-B loads per node).
+//   child >= 0: MeshNode4 index (mesh-relative); child < 0: leaf, payload = ~child =
+//   (first_triangle << 2) | (count - 1); absent: kEmptyChild with an inverted box.
+struct B2_ALIGN(16) MeshNode4 {
+  float lox[4], loy[4], loz[4];
+  float hix[4], hiy[4], hiz[4];
+  int32_t child[4];
+  int32_t pad[4];
+};
+static_assert(sizeof(MeshNode4) == 128, "MeshNode4 must be 128 B");
+
 // The geom BVH is a wide tree (fanout <= 32) so that one warp tests all children of a node at
 // once, one lane per child.  A child slot holds the child's box and its link
 // (>= 0: wide node id, < 0: ~geom id).  Slots of one node are contiguous.
@@ -84,7 +97,7 @@ struct B2_ALIGN(16) MeshTri {
 static_assert(sizeof(MeshTri) == 48, "MeshTri must be 48 B");
 
 struct MeshInfo {
-  int32_t node_base;  // first BvhNode of this mesh in the mesh-node array
+  int32_t node_base;  // first MeshNode4 of this mesh in the mesh-node array
   int32_t tri_base;   // first MeshTri of this mesh
   int32_t nnode;
   int32_t ntri;
@@ -125,7 +138,7 @@ struct CastParams {
   const GeomStatic* gstat;  // [ngeom]
   const int32_t* plane_ids; // [nplane] geoms kept outside the BVH
   const MeshInfo* mesh;     // [nmesh]
-  const BvhNode* mnodes;
+  const MeshNode4* mnodes;  // fanout-4 triangle BVHs of all meshes
   const MeshTri* mtris;
   int32_t nslot, nwnode, ngeom, nplane, nworld;
   // sensor

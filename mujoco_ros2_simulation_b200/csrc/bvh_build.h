@@ -35,6 +35,12 @@ struct WideBvh {
 };
 WideBvh collapse_wide(const BuiltBvh& bvh2);
 
+// Fanout-4 tree collapsed from a BVH2 whose leaves carry triangle ranges (the per-mesh BVHs):
+// starting from a node's two children, the inner child with the largest surface area is replaced
+// by its own children until there are four or none can be opened.  Node 0 = root, pre-order.
+// depth (out): nodes on the longest root-to-leaf path.
+std::vector<MeshNode4> collapse4(const std::vector<BvhNode>& nodes2, int* depth);
+
 // prims: one box per primitive.  max_leaf: primitives per leaf (1 for geoms, <=4 for triangles).
 // leaf_payload_geom: true  -> leaf payload = primitive id (max_leaf must be 1)
 //                    false -> leaf payload = (first << 2) | (count - 1) into `order`

@@ -299,7 +299,7 @@ __global__ void __launch_bounds__(kMeshThreads, B2_MESH_MINBLOCKS)
   double lpnt[3], lvec[3], b0[3], b1[3], x = -1;
   RayF rf;
   float tmax = 0.f;
-  const BvhNode* nodes = nullptr;
+  const MeshNode4* nodes = nullptr;
   const MeshTri* tris = nullptr;
   int32_t cur = kDone;
   int32_t stack[kMeshStack];
@@ -348,27 +348,43 @@ __global__ void __launch_bounds__(kMeshThreads, B2_MESH_MINBLOCKS)
 
     // (2) inner nodes until this lane stands on a leaf (cur < 0) or has nothing left (kDone)
     while (have && cur >= 0) {
-      const BvhNode n = ld_node(nodes + cur);
-      float t0, t1;
-      const bool h0 = n.c0 != kEmptyChild && slab_test(rf, n.lo0, n.hi0, tmax, t0);
-      const bool h1 = n.c1 != kEmptyChild && slab_test(rf, n.lo1, n.hi1, tmax, t1);
-      if (h0 && h1) {
-        const bool first0 = t0 <= t1;
-        if (sp < kMeshStack) {
-          stack[sp] = first0 ? n.c1 : n.c0;
-          stack_t[sp] = first0 ? t1 : t0;
-          sp++;
-#ifdef B2_MESH_PREFETCH
-          // the postponed child will be popped later: start its fetch now (inner nodes only)
-          if (stack[sp - 1] >= 0)
-            asm volatile("prefetch.global.L1 [%0];" ::"l"(nodes + stack[sp - 1]));
-#endif
+      const MeshNode4 n = ld_node4(nodes + cur);
+      float t[4];
+      int32_t lk[4];
+#pragma unroll
+      for (int c = 0; c < 4; c++) {
+        const float lo[3] = {n.lox[c], n.loy[c], n.loz[c]}, hi[3] = {n.hix[c], n.hiy[c], n.hiz[c]};
+        float tc;
+        const bool h = n.child[c] != kEmptyChild && slab_test(rf, lo, hi, tmax, tc);
+        t[c] = h ? tc : INFINITY;
+        lk[c] = n.child[c];
+      }
+      // sort the four (entry distance, link) by distance; missed children (inf) end up last
+#define B2_CAS(i, j)                      \
+  {                                       \
+    const bool sw = t[j] < t[i];          \
+    const float ta = sw ? t[j] : t[i];    \
+    const float tb = sw ? t[i] : t[j];    \
+    const int32_t la = sw ? lk[j] : lk[i]; \
+    const int32_t lb = sw ? lk[i] : lk[j]; \
+    t[i] = ta;                            \
+    t[j] = tb;                            \
+    lk[i] = la;                           \
+    lk[j] = lb;                           \
+  }
+      B2_CAS(0, 1) B2_CAS(2, 3) B2_CAS(0, 2) B2_CAS(1, 3) B2_CAS(1, 2)
+#undef B2_CAS
+      if (t[0] < INFINITY) {
+        // enter the nearest; the others wait on the stack, farthest first
+#pragma unroll
+        for (int c = 3; c >= 1; c--) {
+          if (t[c] < INFINITY && sp < kMeshStack) {
+            stack[sp] = lk[c];
+            stack_t[sp] = t[c];
+            sp++;
+          }
         }
-        cur = first0 ? n.c0 : n.c1;
-      } else if (h0) {
-        cur = n.c0;
-      } else if (h1) {
-        cur = n.c1;
+        cur = lk[0];
       } else {
         cur = kDone;
         while (sp > 0) {

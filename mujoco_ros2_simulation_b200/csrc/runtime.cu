@@ -102,7 +102,7 @@ struct b2_scene {
   DevBuf<GeomStatic> d_gstat;
   DevBuf<int32_t> d_plane_ids;
   DevBuf<MeshInfo> d_mesh;
-  DevBuf<BvhNode> d_mnodes;
+  DevBuf<MeshNode4> d_mnodes;
   DevBuf<MeshTri> d_mtris;
   long long n_mesh_nodes = 0, n_mesh_tris = 0;
   // device: per world
@@ -176,7 +176,7 @@ int build_meshes(b2_scene* s, const b2_model_desc* m) {
     B2_CUDA(cudaMemcpy(s->d_mesh.ptr, hmesh.infos.data(), hmesh.infos.size() * sizeof(MeshInfo),
                        cudaMemcpyHostToDevice));
     B2_CUDA(s->d_mnodes.reserve(hmesh.nodes.size() + 1));
-    B2_CUDA(cudaMemcpy(s->d_mnodes.ptr, hmesh.nodes.data(), hmesh.nodes.size() * sizeof(BvhNode),
+    B2_CUDA(cudaMemcpy(s->d_mnodes.ptr, hmesh.nodes.data(), hmesh.nodes.size() * sizeof(MeshNode4),
                        cudaMemcpyHostToDevice));
     B2_CUDA(s->d_mtris.reserve(hmesh.tris.size() + 1));
     if (!hmesh.tris.empty())

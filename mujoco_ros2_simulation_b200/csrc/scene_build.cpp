@@ -69,26 +69,29 @@ bool build_mesh_bvhs(int nmesh, const int32_t* vertadr, const int32_t* vertnum,
     mi.node_base = (int32_t)out.nodes.size();
     mi.tri_base = (int32_t)out.tris.size();
     mi.ntri = nf;
-    if (nf == 0) {  // empty mesh: a root with two absent children
-      BvhNode root{};
-      for (int j = 0; j < 3; j++) {
-        root.lo0[j] = root.lo1[j] = FLT_MAX;
-        root.hi0[j] = root.hi1[j] = -FLT_MAX;
+    if (nf == 0) {  // empty mesh: a root with four absent children
+      MeshNode4 root{};
+      for (int c = 0; c < 4; c++) {
+        root.lox[c] = root.loy[c] = root.loz[c] = FLT_MAX;
+        root.hix[c] = root.hiy[c] = root.hiz[c] = -FLT_MAX;
+        root.child[c] = kEmptyChild;
       }
-      root.c0 = root.c1 = kEmptyChild;
       mi.nnode = 1;
       out.nodes.push_back(root);
       out.infos[k] = mi;
       continue;
     }
     BuiltBvh bvh = build_bvh(boxes, max_leaf, false, 3.0f);
-    if (bvh.max_depth > max_depth) {
+    int depth4 = 0;
+    const std::vector<MeshNode4> n4 = collapse4(bvh.nodes, &depth4);
+    // every visited node pushes at most three postponed children
+    if (3 * depth4 + 1 > max_depth) {
       err = "mesh BVH deeper than the traversal stack";
       return false;
     }
-    mi.nnode = (int32_t)bvh.nodes.size();
+    mi.nnode = (int32_t)n4.size();
     out.infos[k] = mi;
-    out.nodes.insert(out.nodes.end(), bvh.nodes.begin(), bvh.nodes.end());
+    out.nodes.insert(out.nodes.end(), n4.begin(), n4.end());
     for (int i = 0; i < nf; i++) {
       const int f = bvh.order[i];
       MeshTri t;

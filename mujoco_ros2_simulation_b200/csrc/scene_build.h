@@ -23,7 +23,7 @@ struct HostModel {
 
 struct HostMeshes {
   std::vector<MeshInfo> infos;
-  std::vector<BvhNode> nodes;
+  std::vector<MeshNode4> nodes;  // fanout-4 trees of all meshes, MeshInfo::node_base apart
   std::vector<MeshTri> tris;
 };
 

@@ -15,7 +15,7 @@ _ROOT = os.path.abspath(os.path.join(_HERE, "..", ".."))
 _CSRC = os.path.join(_ROOT, "mujoco_ros2_simulation_b200", "csrc")
 _SO = os.path.join(_HERE, "_build", "libb2emu.so")
 _SRCS = [os.path.join(_HERE, "emu.cpp"), os.path.join(_CSRC, "scene_build.cpp"),
-         os.path.join(_CSRC, "bvh_build.cpp")]
+         os.path.join(_CSRC, "bvh_build.cpp"), os.path.join(_CSRC, "bvh_collapse4.cpp")]
 _DEPS = _SRCS + [os.path.join(_CSRC, f) for f in ("ray_core.cuh", "b2_types.h", "bvh_build.h",
                                                     "scene_build.h")]
 
