@@ -39,7 +39,10 @@ namespace b2 {
 
 constexpr int kMeshStack = 64;    // mesh-BVH stack entries per lane
 constexpr int kQueueCap = 160;    // collect frontier (wide node ids) per warp: 1 + 31 * depth
-constexpr int kCandCap = 96;      // candidate geoms per tile between two drains
+#ifndef B2_CAND_CAP
+#define B2_CAND_CAP 96
+#endif
+constexpr int kCandCap = B2_CAND_CAP;  // candidate geoms per group between two drains
 
 struct B2_ALIGN(16) F4 {
   float x, y, z, w;

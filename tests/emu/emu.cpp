@@ -245,8 +245,9 @@ int emu_bvh_stats(const b2_model_desc* m, const double* xpos, const double* xmat
 // Property check of the tile cone (tests): builds the cone of `n` rays from one origin exactly as
 // trace_tile does (here with a serial reduction) and counts boxes some ray's slab test touches but
 // cone_box rejects.  Must be 0: the collect phase may never drop a box a lane needs.
-int emu_cone_violations(const double pnt[3], const double* vec, int n, const float* boxes,
-                        int nbox) {
+// kept / touched (nullable): boxes the bound keeps / boxes some ray's slab test touches (tightness)
+int emu_cone_check(const double pnt[3], const double* vec, int n, const float* boxes, int nbox,
+                   int* kept, int* ntouched) {
   TileCone tc;
   float sx = 0, sy = 0, sz = 0;
   std::vector<float> df((size_t)n * 3);
@@ -297,8 +298,15 @@ int emu_cone_violations(const double pnt[3], const double* vec, int n, const flo
       }
     }
     if (touched && !keep) bad++;
+    if (kept && keep) ++*kept;
+    if (ntouched && touched) ++*ntouched;
   }
   return bad;
+}
+
+int emu_cone_violations(const double pnt[3], const double* vec, int n, const float* boxes,
+                        int nbox) {
+  return emu_cone_check(pnt, vec, n, boxes, nbox, nullptr, nullptr);
 }
 
 }  // extern "C"

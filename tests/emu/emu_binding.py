@@ -16,7 +16,7 @@ _CSRC = os.path.join(_ROOT, "mujoco_ros2_simulation_b200", "csrc")
 _SO = os.path.join(_HERE, "_build", "libb2emu.so")
 _SRCS = [os.path.join(_HERE, "emu.cpp"), os.path.join(_CSRC, "scene_build.cpp"),
          os.path.join(_CSRC, "bvh_build.cpp"), os.path.join(_CSRC, "bvh_collapse4.cpp")]
-_DEPS = _SRCS + [os.path.join(_CSRC, f) for f in ("ray_core.cuh", "b2_types.h", "bvh_build.h",
+_DEPS = _SRCS + [os.path.join(_CSRC, f) for f in ("ray_core.cuh", "tile_trace.cuh", "b2_types.h", "bvh_build.h",
                                                     "scene_build.h")]
 
 
@@ -122,3 +122,17 @@ def cone_violations(pnt, vec, boxes) -> int:
     L.emu_cone_violations.restype = C.c_int
     L.emu_cone_violations.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int]
     return L.emu_cone_violations(_p(pnt), _p(vec), vec.shape[0], _p(boxes), boxes.shape[0])
+
+
+def cone_counts(pnt, vec, boxes):
+    """(violations, kept, touched): boxes the group bound keeps vs boxes some ray's slab test touches."""
+    pnt = np.ascontiguousarray(pnt, np.float64).reshape(3)
+    vec = np.ascontiguousarray(vec, np.float64).reshape(-1, 3)
+    boxes = np.ascontiguousarray(boxes, np.float32).reshape(-1, 6)
+    L = lib()
+    kept, touched = C.c_int(0), C.c_int(0)
+    L.emu_cone_check.restype = C.c_int
+    L.emu_cone_check.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+    bad = L.emu_cone_check(_p(pnt), _p(vec), vec.shape[0], _p(boxes), boxes.shape[0], C.byref(kept),
+                           C.byref(touched))
+    return bad, kept.value, touched.value

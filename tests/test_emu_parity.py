@@ -153,3 +153,27 @@ def test_tile_cone_is_conservative(emu):
         boxes = np.concatenate([cen - half, cen + half], axis=1).astype(np.float32)
         total += emu.cone_violations(origin, vec, boxes)
     assert total == 0
+
+
+def test_group_cone_on_lidar_shaped_groups(emu):
+    """the device's group shape (32 azimuths x 4 scan lines of the 64x2048 lidar, 128 rays) against
+    the cluttered scene's own geom boxes: the cone never drops a touched box and keeps a bounded
+    surplus (measured: ~10 kept for ~5 touched per group; a 4-plane pyramid would keep ~7 but cost
+    as many instructions as it saved -- profiles/r01_sweeps.txt)."""
+    cs = scenes.clutter500()
+    m, P = cs.model, cs.poses
+    pos = P.geom_xpos.reshape(-1, m.ngeom, 3)[0]
+    R = np.abs(P.geom_xmat.reshape(-1, m.ngeom, 3, 3)[0])
+    ext = np.einsum("gij,gj->gi", R, np.abs(m.geom_size).max(1, keepdims=True).repeat(3, 1) * 1.8)
+    sel = m.geom_type != 0
+    boxes = np.concatenate([pos - ext, pos + ext], 1)[sel].astype(np.float32)
+    D = cs.lidar.local_dir.reshape(64, 2048, 3)
+    rng = np.random.default_rng(5)
+    bad = kept = touched = 0
+    for _ in range(120):
+        row, col = int(rng.integers(0, 16)), int(rng.integers(0, 64))
+        vec = D[row * 4:row * 4 + 4, col * 32:col * 32 + 32].reshape(-1, 3)
+        b, k, t = emu.cone_counts(cs.sensor_pos, vec, boxes)
+        bad, kept, touched = bad + b, kept + k, touched + t
+    assert bad == 0
+    assert touched > 0 and kept <= 3.0 * touched + 120
