@@ -128,9 +128,25 @@ struct MeshSplit {
 };
 constexpr unsigned long long kInfBits = 0x7ff0000000000000ull;
 
+// Scratch of the two-kernel cast (K2a collect -> K2b drain).  K2a writes, per group of tiles, the
+// distance-sorted list of candidate geoms (as child-slot indices of the geom BVH); K2b walks it per
+// tile.  A group K2a cannot finish in one pass (candidate overflow, rays outside the float range)
+// gets count = -1 and is appended to ovf_list: the fused kernel traces those groups.
+struct B2_ALIGN(8) CandRef {
+  float key2;    // squared distance from the origin to the candidate's box, rounded down
+  int32_t slot;  // child slot of the world's geom BVH (box, ~geom id, geom type)
+};
+struct CastLists {
+  int32_t* count;     // [ngroup] candidates of the group, or -1
+  CandRef* list;      // [ngroup][kCandCap]
+  int32_t* ovf_list;  // [ngroup] groups left to the fused kernel
+  int32_t* counters;  // [4] novf, tile cursor (K2b), group cursor (fused fallback), unused
+};
+
 // Everything one cast launch reads.  Passed by value as a __grid_constant__ kernel parameter.
 struct CastParams {
   MeshSplit ms;  // used when the launch splits the mesh work off (ms.counters != nullptr)
+  CastLists cl;  // used by the two-kernel cast (cl.count != nullptr)
   // scene mirror
   const WideChild* wslots;  // [nworld][nslot] geom BVH child slots (boxes refit per step)
   const WideNode* wnodes;   // [nwnode] geom BVH topology (node 0 = root)

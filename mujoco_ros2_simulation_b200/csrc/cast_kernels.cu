@@ -268,6 +268,182 @@ __global__ void __launch_bounds__(kCastThreads, B2_CAST_MINBLOCKS)
 }
 
 // ---------------------------------------------------------------------------------------------
+// Two-kernel cast (split_trace.cuh): K2a collect_kernel -> K2b drain_kernel (+ fused fall-back)
+// ---------------------------------------------------------------------------------------------
+#ifndef B2_COLLECT_MINBLOCKS
+#define B2_COLLECT_MINBLOCKS 3
+#endif
+#ifndef B2_DRAIN_MINBLOCKS
+#define B2_DRAIN_MINBLOCKS 2
+#endif
+
+struct CollectScratch {
+  F4 cand_a[kCandCap];  // unit directions of the group's rays while the cone is built
+  CandRef cref[kCandCap];
+  int32_t queue[kQueueCap];
+  int32_t order[kCandCap];
+};
+
+struct CollectWarp {
+  CollectScratch* s;
+  int lane_;
+  __device__ __forceinline__ int size() const { return 32; }
+  __device__ __forceinline__ int lane() const { return lane_; }
+  __device__ __forceinline__ unsigned lanemask_lt() const { return (1u << lane_) - 1u; }
+  __device__ __forceinline__ unsigned ballot(bool pred) const {
+    return __ballot_sync(0xffffffffu, pred);
+  }
+  __device__ __forceinline__ bool any(bool pred) const { return __any_sync(0xffffffffu, pred); }
+  __device__ __forceinline__ int popc(unsigned m) const { return __popc(m); }
+  __device__ __forceinline__ void sync() const { __syncwarp(); }
+  __device__ __forceinline__ float sum(float v) const {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+  }
+  __device__ __forceinline__ float min(float v) const {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fminf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+  }
+  __device__ __forceinline__ float max(float v) const {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+  }
+  __device__ __forceinline__ int32_t* queue() const { return s->queue; }
+  __device__ __forceinline__ F4* cand_a() const { return s->cand_a; }
+  __device__ __forceinline__ CandRef* cref() const { return s->cref; }
+  __device__ __forceinline__ int32_t* order() const { return s->order; }
+};
+
+// K2a: one warp per group of tiles; same tiling / persistent group fetch as cast_kernel
+template <int MODE, bool STAGE>
+__global__ void __launch_bounds__(kCastThreads, B2_COLLECT_MINBLOCKS)
+    collect_kernel(const __grid_constant__ CastParams p, const TileGeom tg) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  CollectScratch* scratch = reinterpret_cast<CollectScratch*>(smem_raw);
+  unsigned char* s_stage = smem_raw + kCastWarps * sizeof(CollectScratch);
+  const int warp_id = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int scan_b = tg.dynamic ? 0 : blockIdx.x / tg.chunks_per_scan;
+  const int chunk = blockIdx.x - scan_b * tg.chunks_per_scan;
+  const int world = p.scan_world ? p.scan_world[scan_b] : (p.scan0 + scan_b) % p.nworld;
+  const WideChild* wslots = p.wslots + (size_t)world * p.nslot;
+  const WideNode* wnodes = p.wnodes;
+  const uint8_t* elim = p.elim;
+  if (STAGE) {
+    const float4* src = reinterpret_cast<const float4*>(wslots);
+    float4* dst = reinterpret_cast<float4*>(s_stage);
+    for (int i = threadIdx.x; i < p.nslot * 2; i += kCastThreads) dst[i] = __ldg(src + i);
+    int2* ndst = reinterpret_cast<int2*>(s_stage + (size_t)p.nslot * sizeof(WideChild));
+    const int2* nsrc = reinterpret_cast<const int2*>(p.wnodes);
+    for (int i = threadIdx.x; i < p.nwnode; i += kCastThreads) ndst[i] = __ldg(nsrc + i);
+    const size_t bvh = (size_t)p.nslot * sizeof(WideChild) + (size_t)p.nwnode * sizeof(WideNode);
+    uint8_t* edst = s_stage + ((bvh + 15) & ~(size_t)15);
+    for (int i = threadIdx.x; i < p.ngeom; i += kCastThreads) edst[i] = __ldg(p.elim + i);
+    __syncthreads();
+    wslots = reinterpret_cast<const WideChild*>(s_stage);
+    wnodes = reinterpret_cast<const WideNode*>(ndst);
+    elim = edst;
+  }
+  const GeomPose* pose = p.pose + (size_t)world * p.ngeom;
+  CollectWarp warp{scratch + warp_id, lane};
+  const float tcap = (MODE == MODE_MULTIRAY) ? f32_up(p.cutoff) : FLT_MAX;
+
+  for (int t = warp_id * kGroupTiles;; t += kCastWarps * kGroupTiles) {
+    int scan, tile0, nt;
+    if (tg.dynamic) {
+      int g = 0;
+      if (lane == 0) g = atomicAdd(p.work_counter, 1);
+      g = __shfl_sync(0xffffffffu, g, 0);
+      if (g >= tg.ngroups) break;
+      scan = g / tg.groups_per_scan;
+      tile0 = (g - scan * tg.groups_per_scan) * kGroupTiles;
+      nt = ::min(kGroupTiles, tg.tiles_per_scan - tile0);
+    } else {
+      if (t >= tg.tiles_per_block) break;
+      scan = scan_b;
+      tile0 = chunk * tg.tiles_per_block + t;
+      if (tile0 >= tg.tiles_per_scan) break;  // warp-uniform
+      nt = ::min(kGroupTiles, ::min(tg.tiles_per_block - t, tg.tiles_per_scan - tile0));
+    }
+    double o[3];
+#pragma unroll
+    for (int k = 0; k < 3; k++) o[k] = __ldg(p.spos + (size_t)scan * 3 + k);
+    const GroupGen<MODE> gen{p, tg, scan, tile0, lane};
+    const int gid = scan * tg.groups_per_scan + tile0 / kGroupTiles;
+    const int n = collect_group<STAGE>(p, wslots, wnodes, elim, pose, nt, o, tcap, warp, gen,
+                                       p.cl.list + (size_t)gid * kCandCap);
+    if (lane == 0) {
+      p.cl.count[gid] = n;
+      if (n < 0) p.cl.ovf_list[atomicAdd(p.cl.counters + 0, 1)] = gid;
+    }
+  }
+}
+
+// K2b: persistent; one warp per tile, fetched from a global cursor.  No shared memory.
+template <int MODE, bool SPLIT>
+__global__ void __launch_bounds__(kCastThreads, B2_DRAIN_MINBLOCKS)
+    drain_kernel(const __grid_constant__ CastParams p, const TileGeom tg) {
+  const int lane = threadIdx.x & 31;
+  DevWarp<SPLIT> warp{nullptr, lane, -1};
+  const float tcap = (MODE == MODE_MULTIRAY) ? f32_up(p.cutoff) : FLT_MAX;
+  const long long ntile = (long long)p.nscan * tg.tiles_per_scan;
+  for (;;) {
+    int tile = 0;
+    if (lane == 0) tile = atomicAdd(p.cl.counters + 1, 1);
+    tile = __shfl_sync(0xffffffffu, tile, 0);
+    if (tile >= ntile) break;
+    const int scan = tile / tg.tiles_per_scan;
+    const int ti = tile - scan * tg.tiles_per_scan;
+    const int gid = scan * tg.groups_per_scan + ti / kGroupTiles;
+    const int count = __ldg(p.cl.count + gid);
+    if (count < 0) continue;  // left to the fused kernel
+    const int world = p.scan_world ? p.scan_world[scan] : (p.scan0 + scan) % p.nworld;
+    const WideChild* wslots = p.wslots + (size_t)world * p.nslot;
+    const GeomPose* pose = p.pose + (size_t)world * p.ngeom;
+    double o[3];
+#pragma unroll
+    for (int k = 0; k < 3; k++) o[k] = __ldg(p.spos + (size_t)scan * 3 + k);
+    const GroupGen<MODE> gen{p, tg, scan, ti, lane};
+    const GroupEpi<MODE, SPLIT> epi{p, tg, scan, ti, lane};
+    drain_tile(p, wslots, p.elim, pose, 0, o, tcap, warp, gen, epi, count,
+               p.cl.list + (size_t)gid * kCandCap);
+  }
+}
+
+// the groups K2a could not finish: fused trace_group, unstaged, one warp per listed group
+template <int MODE, bool SPLIT>
+__global__ void __launch_bounds__(kCastThreads, B2_CAST_MINBLOCKS)
+    fallback_kernel(const __grid_constant__ CastParams p, const TileGeom tg) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int novf = p.cl.counters[0];
+  if (novf == 0) return;
+  WarpScratch* scratch = reinterpret_cast<WarpScratch*>(smem_raw);
+  const int warp_id = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  DevWarp<SPLIT> warp{scratch + warp_id, lane, -1};
+  const float tcap = (MODE == MODE_MULTIRAY) ? f32_up(p.cutoff) : FLT_MAX;
+  for (;;) {
+    int idx = 0;
+    if (lane == 0) idx = atomicAdd(p.cl.counters + 2, 1);
+    idx = __shfl_sync(0xffffffffu, idx, 0);
+    if (idx >= novf) break;
+    const int gid = p.cl.ovf_list[idx];
+    const int scan = gid / tg.groups_per_scan;
+    const int tile0 = (gid - scan * tg.groups_per_scan) * kGroupTiles;
+    const int nt = ::min(kGroupTiles, tg.tiles_per_scan - tile0);
+    const int world = p.scan_world ? p.scan_world[scan] : (p.scan0 + scan) % p.nworld;
+    double o[3];
+#pragma unroll
+    for (int k = 0; k < 3; k++) o[k] = __ldg(p.spos + (size_t)scan * 3 + k);
+    const GroupGen<MODE> gen{p, tg, scan, tile0, lane};
+    const GroupEpi<MODE, SPLIT> epi{p, tg, scan, tile0, lane};
+    trace_group<false>(p, p.wslots + (size_t)world * p.nslot, p.wnodes, p.elim,
+                       p.pose + (size_t)world * p.ngeom, nt, o, tcap, warp, gen, epi);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // K2b: one thread per (ray, mesh geom) pair
 // ---------------------------------------------------------------------------------------------
 //
@@ -478,6 +654,27 @@ static cudaError_t launch_tile_kernel(K k, const CastParams& p, const TileGeom& 
   return cudaGetLastError();
 }
 
+// K2a -> K2b -> fused fall-back for the groups K2a gave up on
+template <int MODE, bool SPLIT>
+static cudaError_t launch_two_kernel(const CastParams& p, const TileGeom& tg, bool stage,
+                                     long long nblocks_static, int sm_count, cudaStream_t stream) {
+  cudaError_t err = cudaMemsetAsync(p.cl.counters, 0, 4 * sizeof(int32_t), stream);
+  if (err != cudaSuccess) return err;
+  size_t smem = kCastWarps * sizeof(CollectScratch);
+  if (stage) smem += cast_stage_bytes(p.nslot, p.nwnode, p.ngeom);
+  const unsigned cgrid =
+      tg.dynamic ? (unsigned)(sm_count * B2_COLLECT_MINBLOCKS) : (unsigned)nblocks_static;
+  err = stage ? launch_tile_kernel(collect_kernel<MODE, true>, p, tg, cgrid, smem, stream)
+              : launch_tile_kernel(collect_kernel<MODE, false>, p, tg, cgrid, smem, stream);
+  if (err != cudaSuccess) return err;
+  drain_kernel<MODE, SPLIT><<<(unsigned)(sm_count * B2_DRAIN_MINBLOCKS), kCastThreads, 0, stream>>>(
+      p, tg);
+  err = cudaGetLastError();
+  if (err != cudaSuccess) return err;
+  return launch_tile_kernel(fallback_kernel<MODE, SPLIT>, p, tg, (unsigned)sm_count,
+                            kCastWarps * sizeof(WarpScratch), stream);
+}
+
 template <int MODE>
 static cudaError_t launch_cast_mode(const CastParams& p, bool stage, int tiles_per_block,
                                     int sm_count, cudaStream_t stream, int* nlaunch) {
@@ -515,7 +712,12 @@ static cudaError_t launch_cast_mode(const CastParams& p, bool stage, int tiles_p
     err = cudaMemsetAsync(p.work_counter, 0, sizeof(int32_t), stream);
     if (err != cudaSuccess) return err;
   }
+  const bool two = p.cl.count != nullptr;
   if (!split) {
+    if (two) {
+      *nlaunch += 3;
+      return launch_two_kernel<MODE, false>(p, tg, stage, nblocks_static, sm_count, stream);
+    }
     err = stage ? launch_tile_kernel(cast_kernel<MODE, true, false, false>, p, tg, (unsigned)nblocks,
                                      smem, stream)
                 : launch_tile_kernel(cast_kernel<MODE, false, false, false>, p, tg,
@@ -525,10 +727,15 @@ static cudaError_t launch_cast_mode(const CastParams& p, bool stage, int tiles_p
   }
   err = cudaMemsetAsync(p.ms.counters, 0, 4 * sizeof(int32_t), stream);
   if (err != cudaSuccess) return err;
-  err = stage ? launch_tile_kernel(cast_kernel<MODE, true, true, false>, p, tg, (unsigned)nblocks,
-                                   smem, stream)
-              : launch_tile_kernel(cast_kernel<MODE, false, true, false>, p, tg, (unsigned)nblocks,
-                                   smem, stream);
+  if (two) {
+    *nlaunch += 2;
+    err = launch_two_kernel<MODE, true>(p, tg, stage, nblocks_static, sm_count, stream);
+  } else {
+    err = stage ? launch_tile_kernel(cast_kernel<MODE, true, true, false>, p, tg, (unsigned)nblocks,
+                                     smem, stream)
+                : launch_tile_kernel(cast_kernel<MODE, false, true, false>, p, tg,
+                                     (unsigned)nblocks, smem, stream);
+  }
   if (err != cudaSuccess) return err;
   const unsigned mgrid = (unsigned)(sm_count * 16);
   mesh_pairs_kernel<MODE><<<mgrid, kMeshThreads, 0, stream>>>(p);

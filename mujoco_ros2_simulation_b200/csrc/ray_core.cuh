@@ -443,6 +443,25 @@ B2_LEAF double prim_test(int type, const GeomPose* gp, const GeomStatic* gsp, do
   }
 }
 
+// prim_test(GEOM_PLANE, ...) inline: the same arithmetic without the call, for kernels that test
+// nothing but planes (K2a) or test them outside the candidate loop (K2b)
+B2_HD double plane_test(const GeomPose* gp, const GeomStatic* gsp, const double pnt[3],
+                        const double vec[3]) {
+  const GeomPose P = ld_pose(gp);
+  const GeomStatic gs = ld_gstat(gsp);
+  if (gs.size[0] <= 0 && gs.size[1] <= 0) {
+    const double d0 = pnt[0] - P.pos[0], d1 = pnt[1] - P.pos[1], d2 = pnt[2] - P.pos[2];
+    const double lpz = P.mat[2] * d0 + P.mat[5] * d1 + P.mat[8] * d2;
+    const double lvz = P.mat[2] * vec[0] + P.mat[5] * vec[1] + P.mat[8] * vec[2];
+    if (lvz > -kMinVal) return -1;
+    const double x = -lpz / lvz;
+    return x < 0 ? -1 : x;
+  }
+  double lpnt[3], lvec[3];
+  ray_map(P, pnt, vec, lpnt, lvec);
+  return local_plane(gs.size, lpnt, lvec);
+}
+
 // ---------------------------------------------------------------------------------------------
 // mesh triangle test (A.4)
 // ---------------------------------------------------------------------------------------------

@@ -123,6 +123,9 @@ struct b2_scene {
   DevBuf<double> d_pair_x;
   DevBuf<uint32_t> d_aff_ray;
   DevBuf<unsigned long long> d_aff_bits, d_aff_prim;
+  // scratch of the two-kernel cast: per-group candidate lists
+  DevBuf<int32_t> d_cl_count, d_cl_ovf;
+  DevBuf<CandRef> d_cl_list;
   bool has_mesh_geoms = false;
   // The plugin's physics, lidar and camera threads share one scene: every enqueue on the scene's
   // stream (and every use of the scene-owned scratch) is serialised by this mutex.
@@ -291,13 +294,29 @@ int run_cast(b2_scene* s, CastParams p, cudaStream_t stream) {
   if (force == 1 && s->has_mesh_geoms) split = true;
   int scans_per_chunk = p.nscan;
   // counters[0..3]: split mesh path; counters[4]: group cursor of a persistent K2 launch
-  B2_CUDA(s->d_counters.reserve(8));
+  // counters[8..11]: the two-kernel cast (CastLists)
+  B2_CUDA(s->d_counters.reserve(16));
   p.work_counter = env_int("B2_DYNAMIC", 1) != 0 ? s->d_counters.ptr + 4 : nullptr;
-  if (split) {
-    // measured on B200 (profiles/r01_sweeps.txt): 8M rays/chunk 5.0, 32M 5.4, whole launch 5.6
-    // Grays/s -- fewer, longer kernels lose less in launch gaps and tails; scratch is 68 B/ray
-    const long long chunk_rays = env_int("B2_CHUNK_MRAYS", 144) * 1000000LL;
+  // two-kernel cast (K2a collect -> K2b drain): large launches on scenes with a geom BVH
+  const bool two = env_int("B2_TWO_KERNEL", 1) != 0 && s->nwnode > 0 && total >= 65536;
+  // measured on B200 (profiles/r01_sweeps.txt): 8M rays/chunk 5.0, 32M 5.4, whole launch 5.6
+  // Grays/s -- fewer, longer kernels lose less in launch gaps and tails; scratch is 68 B/ray
+  const long long chunk_rays = env_int("B2_CHUNK_MRAYS", 144) * 1000000LL;
+  if (split || two)
     scans_per_chunk = (int)std::max(1LL, std::min((long long)p.nscan, chunk_rays / p.nray));
+  p.cl = CastLists{};
+  if (two) {
+    const size_t groups_per_scan = ((size_t)cast_tiles_per_scan(p.nray) + kGroupTiles - 1) / kGroupTiles;
+    const size_t ngroup = groups_per_scan * (size_t)scans_per_chunk;
+    B2_CUDA(s->d_cl_count.reserve(ngroup));
+    B2_CUDA(s->d_cl_ovf.reserve(ngroup));
+    B2_CUDA(s->d_cl_list.reserve(ngroup * kCandCap));
+    p.cl.count = s->d_cl_count.ptr;
+    p.cl.ovf_list = s->d_cl_ovf.ptr;
+    p.cl.list = s->d_cl_list.ptr;
+    p.cl.counters = s->d_counters.ptr + 8;
+  }
+  if (split) {
     const size_t aff_cap = (size_t)scans_per_chunk * p.nray;
     const size_t pair_cap = std::min<size_t>(2 * aff_cap + 1024, 0x7fffffff);
     if (aff_cap > 0x7fffffff) return fail(B2_ERR_INVALID, "scan too large for the split mesh path");
@@ -509,6 +528,9 @@ int b2_scene_destroy(b2_scene* s) {
   s->d_aff_prim_id.release();
   s->d_aff_mesh_id.release();
   s->d_counters.release();
+  s->d_cl_count.release();
+  s->d_cl_ovf.release();
+  s->d_cl_list.release();
   s->d_mr_vec.release();
   s->d_mr_dist.release();
   s->d_mr_pnt.release();

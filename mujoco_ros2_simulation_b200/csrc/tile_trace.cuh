@@ -327,4 +327,6 @@ B2_HD void trace_group(const CastParams& p, const WideChild* wslots, const WideN
 }
 
 }  // namespace b2
+
+#include "split_trace.cuh"
 #endif

@@ -21,6 +21,8 @@ using namespace b2;
 
 namespace {
 
+long long g_emu_fallbacks = 0;  // groups the two-kernel emulation left to trace_group
+
 struct HostWarp {
   F4 cand_a_[kCandCap], cand_b_[kCandCap];
   int32_t queue_[kQueueCap], order_[kCandCap];
@@ -41,6 +43,8 @@ struct HostWarp {
   RayState st_[kGroupTiles];
   int slot_ = -1;
   RayState* ray_state() { return st_; }
+  CandRef cref_[kCandCap];
+  CandRef* cref() { return cref_; }
   void set_slot(int v) { slot_ = v; }
   int get_slot() const { return slot_; }
   // the emulation traces meshes in place (the device's clean-up / small-launch policy)
@@ -168,6 +172,23 @@ void run(const EmuScene& S, CastParams& p, const double o[3], const double* R) {
       cast_make_ray(p, p.mode, R, r, l, vec);
       cast_epilogue(p, p.mode, 0, r, hit, l);
     };
+    // B2_EMU_TWO_KERNEL=1: the two-kernel cast (split_trace.cuh) -- collect_group, then drain_tile
+    // per tile, with the fused trace_group for the groups the single collect pass gives up on
+    static const bool two = [] {
+      const char* v = std::getenv("B2_EMU_TWO_KERNEL");
+      return v && std::atoi(v) != 0;
+    }();
+    if (two) {
+      CandRef list[kCandCap];
+      const int n = collect_group<false>(p, p.wslots, p.wnodes, p.elim, p.pose, nt, o, tcap, warp,
+                                         gen, list);
+      if (n >= 0) {
+        for (int t = 0; t < nt; t++)
+          drain_tile(p, p.wslots, p.elim, p.pose, t, o, tcap, warp, gen, epi, n, list);
+        continue;
+      }
+      g_emu_fallbacks++;
+    }
     trace_group<false>(p, p.wslots, p.wnodes, p.elim, p.pose, nt, o, tcap, warp, gen, epi);
   }
 }
@@ -229,6 +250,8 @@ int emu_lidar(const b2_model_desc* m, const double* xpos, const double* xmat,
   run(S, p, pos, mat);
   return 0;
 }
+
+long long emu_fallbacks() { return g_emu_fallbacks; }
 
 // BVH statistics for tests: child slots / depth of the wide geom BVH and total mesh nodes
 int emu_bvh_stats(const b2_model_desc* m, const double* xpos, const double* xmat, int mesh_leaf,
