@@ -273,8 +273,11 @@ __global__ void __launch_bounds__(kCastThreads, B2_CAST_MINBLOCKS)
 #ifndef B2_COLLECT_MINBLOCKS
 #define B2_COLLECT_MINBLOCKS 3
 #endif
+// CTAs/SM of K2b (register cap): 2 / 3 / 4 / 5 = 126 / 80 / 64 / 48 registers measured 7.91 / 8.36 /
+// 8.42 / 7.82 Grays/s -- without shared memory the L1 absorbs the spills and the extra warps hide
+// the fp64 latency (the fused kernel could not make this trade: profiles/r01_sweeps.txt)
 #ifndef B2_DRAIN_MINBLOCKS
-#define B2_DRAIN_MINBLOCKS 2
+#define B2_DRAIN_MINBLOCKS 4
 #endif
 
 struct CollectScratch {

@@ -159,6 +159,8 @@ void run(const EmuScene& S, CastParams& p, const double o[3], const double* R) {
   (void)S;
   HostWarp warp;
   const float tcap = p.mode == MODE_MULTIRAY ? f32_up(p.cutoff) : FLT_MAX;
+  const char* two_env = std::getenv("B2_EMU_TWO_KERNEL");
+  const bool two = two_env && std::atoi(two_env) != 0;
   // groups of kGroupTiles one-ray "tiles": consecutive rays share one collect, as on the device
   for (int r0 = 0; r0 < p.nray; r0 += kGroupTiles) {
     const int nt = p.nray - r0 < kGroupTiles ? p.nray - r0 : kGroupTiles;
@@ -174,10 +176,6 @@ void run(const EmuScene& S, CastParams& p, const double o[3], const double* R) {
     };
     // B2_EMU_TWO_KERNEL=1: the two-kernel cast (split_trace.cuh) -- collect_group, then drain_tile
     // per tile, with the fused trace_group for the groups the single collect pass gives up on
-    static const bool two = [] {
-      const char* v = std::getenv("B2_EMU_TWO_KERNEL");
-      return v && std::atoi(v) != 0;
-    }();
     if (two) {
       CandRef list[kCandCap];
       const int n = collect_group<false>(p, p.wslots, p.wnodes, p.elim, p.pose, nt, o, tcap, warp,

@@ -136,3 +136,10 @@ def cone_counts(pnt, vec, boxes):
     bad = L.emu_cone_check(_p(pnt), _p(vec), vec.shape[0], _p(boxes), boxes.shape[0], C.byref(kept),
                            C.byref(touched))
     return bad, kept.value, touched.value
+
+
+def fallbacks() -> int:
+    """groups the two-kernel emulation (B2_EMU_TWO_KERNEL=1) handed to the fused trace_group so far"""
+    L = lib()
+    L.emu_fallbacks.restype = C.c_longlong
+    return int(L.emu_fallbacks())

@@ -177,3 +177,31 @@ def test_group_cone_on_lidar_shaped_groups(emu):
         bad, kept, touched = bad + b, kept + k, touched + t
     assert bad == 0
     assert touched > 0 and kept <= 3.0 * touched + 120
+
+
+def test_two_kernel_cast_emulated(emu, oracle, monkeypatch):
+    """the two-kernel cast (split_trace.cuh: collect_group -> drain_tile, fused trace_group for the
+    groups the single collect pass gives up on) against the oracle: the clutter scene, and a scene
+    whose candidate lists overflow (200 spheres strung along the rays) so the fall-back runs."""
+    monkeypatch.setenv("B2_EMU_TWO_KERNEL", "1")
+    cs = scenes.clutter500(n_el=16, n_az=128)
+    pos, mat = cs.sensor_poses(2)
+    o = oracle.OracleScene(cs.model, cs.poses)
+    before = emu.fallbacks()
+    for i in range(2):
+        r, g, raw, _ = emu.lidar(cs.model, cs.poses, cs.lidar, pos[i], mat[i])
+        rr, gg, rraw = o.lidar_scan(cs.lidar, pos[i], mat[i], nthread=4)
+        assert np.array_equal(raw, rraw) and np.array_equal(g, gg) and np.array_equal(r, rr)
+    # a string of pearls: every ray's cone holds far more than the candidate cap
+    from mujoco_ros2_simulation_b200.model import GEOM_SPHERE, Model, Poses
+    n = 200
+    gpos = np.stack([1.0 + 0.1 * np.arange(n), 0.02 * np.sin(np.arange(n)), 0.02 * np.cos(np.arange(n))], 1)
+    model = Model(np.full(n, GEOM_SPHERE), np.zeros(n, int), np.zeros(n, int), -np.ones(n, int),
+                  -np.ones(n, int), np.tile([0.03, 0.0, 0.0], (n, 1)), np.ones((n, 4)), np.zeros((0, 4)), [0])
+    poses = Poses(gpos, np.tile(np.eye(3).reshape(1, 9), (n, 1)))
+    rng = np.random.default_rng(3)
+    vec = np.array([1.0, 0, 0])[None] + rng.normal(size=(64, 3)) * 0.01
+    d, g = emu.multiray(model, poses, np.zeros(3), vec)
+    od, og = oracle.OracleScene(model, poses).multi_ray(np.zeros(3), vec)
+    assert np.array_equal(d, od) and np.array_equal(g, og)
+    assert emu.fallbacks() > before

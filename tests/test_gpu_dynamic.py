@@ -1,5 +1,6 @@
-"""GPU tier: the persistent (dynamic group fetch) K2 launch against the static tiling and the
-oracle.  Single-world batches above ~1.2 M rays take the persistent launch (B2_DYNAMIC=0 forces
+"""GPU tier: the launch shapes of K2 against each other and the oracle -- the two-kernel cast
+(collect -> drain, with its fused fall-back) vs the fused kernel, and the persistent (dynamic group
+fetch) launch vs the static tiling.  Single-world batches above ~1.2 M rays take the persistent launch (B2_DYNAMIC=0 forces
 the static one); both must give the same bits, with and without the split mesh path, in every
 mode (lidar / multiRay / camera rays)."""
 import os
@@ -54,8 +55,10 @@ def test_lidar_dynamic_equals_static_and_oracle(oracle, split):
         dyn = _cast_dev(lid, s, pos, mat, xyz=True)
     with _env(B2_DYNAMIC=0, B2_SPLIT=split):
         sta = _cast_dev(lid, s, pos, mat, xyz=True)
-    for a, b in zip(dyn, sta):
-        assert np.array_equal(a, b, equal_nan=True)
+    with _env(B2_TWO_KERNEL=0, B2_SPLIT=split):
+        fused = _cast_dev(lid, s, pos, mat, xyz=True)             # the fused K2 instead of collect -> drain
+    for a, b, c in zip(dyn, sta, fused):
+        assert np.array_equal(a, b, equal_nan=True) and np.array_equal(a, c, equal_nan=True)
     assert (dyn[0] != -7).all() and (dyn[1] != -7.0).all()      # every ray was written
     o = oracle.OracleScene(cs.model, cs.poses)
     for sc in (0, n - 1):
@@ -128,3 +131,37 @@ def test_camera_rays_dynamic():
     assert np.array_equal(outs[0], outs[1])
     assert (outs[0] >= 0).all() and (outs[0] < 1.0).mean() > 0.2
     assert not np.array_equal(outs[0][0], outs[0][5])
+
+
+def test_two_kernel_vs_fused_with_overflowing_groups(oracle):
+    """a dense cluster (every group's candidate list overflows -> fused fall-back kernel), rays whose
+    length is outside the float range (group handed to the fall-back too) and ordinary groups, in one
+    launch above the two-kernel threshold: two-kernel == fused == oracle."""
+    from mujoco_ros2_simulation_b200.model import GEOM_BOX, GEOM_SPHERE, Model, Poses, random_rotations
+    rng = np.random.default_rng(25)
+    n = 400
+    t = rng.choice([GEOM_BOX, GEOM_SPHERE], size=n)
+    pos = rng.normal(size=(n, 3)) * 0.6
+    pos[300:] += np.array([0.0, 30.0, 0.0])          # a second, sparser cluster: ordinary groups
+    pos[300:] *= np.array([1.0, 1.0, 8.0])
+    m = Model(t, np.zeros(n, int), np.zeros(n, int), -np.ones(n, int), -np.ones(n, int),
+              rng.uniform(0.5, 1.5, size=(n, 3)), np.ones((n, 4)), np.zeros((0, 4)), [0])
+    m.geom_size[300:] *= 0.2
+    P = Poses(pos, random_rotations(rng, n).reshape(n, 9))
+    s = engine.Scene(m)
+    s.update_poses(P)
+    nray = 98304
+    az = np.linspace(0, 2 * np.pi, nray, endpoint=False)
+    vec = np.stack([np.cos(az), np.sin(az), 0.05 * np.sin(7 * az)], 1)
+    vec[5000:5040] *= 1e-25                           # |vec|^2 underflows float: no culling for that group
+    vec[70000:70100] *= 1e22
+    pnt = np.array([6.0, 0.5, 0.2])
+    with _env(B2_TWO_KERNEL=1):
+        d2, g2 = s.multiray(pnt, vec)
+    with _env(B2_TWO_KERNEL=0):
+        d1, g1 = s.multiray(pnt, vec)
+    assert np.array_equal(d1, d2) and np.array_equal(g1, g2)
+    sel = np.concatenate([np.arange(0, nray, 37), np.arange(4990, 5050), np.arange(69990, 70110)])
+    od, og = oracle.OracleScene(m, P).multi_ray(pnt, vec[sel], nthread=8)
+    assert np.array_equal(od, d2[sel]) and np.array_equal(og, g2[sel])
+    assert (g2 >= 0).mean() > 0.2

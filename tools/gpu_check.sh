@@ -16,8 +16,10 @@ if [ "${NCU:-1}" = "1" ]; then
   ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file $OUT/launches_$TAG.csv $BCMD > $OUT/ncu_launches_$TAG.log 2>&1
   echo "ncu launches rc=$?"
   $BCMD > $OUT/plain2_$TAG.log 2>&1 && \
-  ncu --set full --clock-control none --import-source on -k regex:cast_kernel -s 4 -c 1 -o $OUT/cast_$TAG $BCMD > $OUT/ncu_full_$TAG.log 2>&1
-  echo "ncu full rc=$?"
+  ncu --set full --clock-control none --import-source on -k regex:drain_kernel -s 4 -c 1 -o $OUT/drain_$TAG $BCMD > $OUT/ncu_drain_$TAG.log 2>&1
+  echo "ncu drain rc=$?"
+  ncu --set full --clock-control none --import-source on -k regex:collect_kernel -s 4 -c 1 -o $OUT/collect_$TAG $BCMD > $OUT/ncu_collect_$TAG.log 2>&1
+  echo "ncu collect rc=$?"
   ncu --set full --clock-control none --import-source on -k regex:mesh_pairs -s 2 -c 1 -o $OUT/mesh_$TAG $BCMD > $OUT/ncu_mesh_$TAG.log 2>&1
   echo "ncu mesh rc=$?"
   if [ "${NCU_DEPTH:-1}" = "1" ]; then ncu --set full --clock-control none --import-source on -k regex:depth_to_cloud -s 3 -c 1 -o $OUT/depth_$TAG $BCMD > $OUT/ncu_depth_$TAG.log 2>&1; echo "ncu depth rc=$?"; fi
