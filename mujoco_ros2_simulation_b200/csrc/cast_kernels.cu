@@ -279,6 +279,12 @@ __global__ void __launch_bounds__(kCastThreads, B2_CAST_MINBLOCKS)
 #ifndef B2_DRAIN_MINBLOCKS
 #define B2_DRAIN_MINBLOCKS 4
 #endif
+// consecutive tiles a warp takes per fetch from the tile cursor: the tiles of one group share the
+// candidate list, so taking them together keeps it in L1 (1 / 2 / 4 / 8 / 16 measured 8.41 / 9.30 /
+// 9.35 / 9.35 / 9.29 Grays/s)
+#ifndef B2_DRAIN_FETCH
+#define B2_DRAIN_FETCH 4
+#endif
 
 struct CollectScratch {
   F4 cand_a[kCandCap];  // unit directions of the group's rays while the cone is built
@@ -393,10 +399,12 @@ __global__ void __launch_bounds__(kCastThreads, B2_DRAIN_MINBLOCKS)
   const float tcap = (MODE == MODE_MULTIRAY) ? f32_up(p.cutoff) : FLT_MAX;
   const long long ntile = (long long)p.nscan * tg.tiles_per_scan;
   for (;;) {
-    int tile = 0;
-    if (lane == 0) tile = atomicAdd(p.cl.counters + 1, 1);
-    tile = __shfl_sync(0xffffffffu, tile, 0);
-    if (tile >= ntile) break;
+    int base = 0;
+    if (lane == 0) base = atomicAdd(p.cl.counters + 1, B2_DRAIN_FETCH);
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (base >= ntile) break;
+#pragma unroll 1
+    for (int tile = base; tile < base + B2_DRAIN_FETCH && tile < ntile; tile++) {
     const int scan = tile / tg.tiles_per_scan;
     const int ti = tile - scan * tg.tiles_per_scan;
     const int gid = scan * tg.groups_per_scan + ti / kGroupTiles;
@@ -412,6 +420,7 @@ __global__ void __launch_bounds__(kCastThreads, B2_DRAIN_MINBLOCKS)
     const GroupEpi<MODE, SPLIT> epi{p, tg, scan, ti, lane};
     drain_tile(p, wslots, p.elim, pose, 0, o, tcap, warp, gen, epi, count,
                p.cl.list + (size_t)gid * kCandCap);
+    }
   }
 }
 
