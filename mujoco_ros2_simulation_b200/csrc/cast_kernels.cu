@@ -279,12 +279,6 @@ __global__ void __launch_bounds__(kCastThreads, B2_CAST_MINBLOCKS)
 #ifndef B2_DRAIN_MINBLOCKS
 #define B2_DRAIN_MINBLOCKS 4
 #endif
-// consecutive tiles a warp takes per fetch from the tile cursor: the tiles of one group share the
-// candidate list, so taking them together keeps it in L1 (1 / 2 / 4 / 8 / 16 measured 8.41 / 9.30 /
-// 9.35 / 9.35 / 9.29 Grays/s)
-#ifndef B2_DRAIN_FETCH
-#define B2_DRAIN_FETCH 4
-#endif
 
 struct CollectScratch {
   F4 cand_a[kCandCap];  // unit directions of the group's rays while the cone is built
@@ -390,37 +384,57 @@ __global__ void __launch_bounds__(kCastThreads, B2_COLLECT_MINBLOCKS)
   }
 }
 
-// K2b: persistent; one warp per tile, fetched from a global cursor.  No shared memory.
+// K2b: persistent; a warp takes one group of tiles per fetch from a global cursor (its tiles share
+// the candidate list, which then stays in L1: per-tile fetch 8.41, per-group 9.62 Grays/s) and reads
+// the list and the slots through L1 -- no shared memory.  B2_DRAIN_STAGED=1 copies the group's
+// candidates to 3 KB of shared memory per warp first, as the fused kernel does: measured slower
+// (8.69), the carve-out costs more L1 than the copies save.
+#ifndef B2_DRAIN_STAGED
+#define B2_DRAIN_STAGED 0
+#endif
 template <int MODE, bool SPLIT>
 __global__ void __launch_bounds__(kCastThreads, B2_DRAIN_MINBLOCKS)
     drain_kernel(const __grid_constant__ CastParams p, const TileGeom tg) {
+#if B2_DRAIN_STAGED
+  __shared__ F4 s_ca[kCastWarps][kCandCap];
+  __shared__ F4 s_cb[kCastWarps][kCandCap];
+  F4* ca = s_ca[threadIdx.x >> 5];
+  F4* cb = s_cb[threadIdx.x >> 5];
+#else
+  F4* ca = nullptr;
+  F4* cb = nullptr;
+#endif
   const int lane = threadIdx.x & 31;
   DevWarp<SPLIT> warp{nullptr, lane, -1};
   const float tcap = (MODE == MODE_MULTIRAY) ? f32_up(p.cutoff) : FLT_MAX;
-  const long long ntile = (long long)p.nscan * tg.tiles_per_scan;
   for (;;) {
-    int base = 0;
-    if (lane == 0) base = atomicAdd(p.cl.counters + 1, B2_DRAIN_FETCH);
-    base = __shfl_sync(0xffffffffu, base, 0);
-    if (base >= ntile) break;
-#pragma unroll 1
-    for (int tile = base; tile < base + B2_DRAIN_FETCH && tile < ntile; tile++) {
-    const int scan = tile / tg.tiles_per_scan;
-    const int ti = tile - scan * tg.tiles_per_scan;
-    const int gid = scan * tg.groups_per_scan + ti / kGroupTiles;
+    int gid = 0;
+    if (lane == 0) gid = atomicAdd(p.cl.counters + 1, 1);
+    gid = __shfl_sync(0xffffffffu, gid, 0);
+    if (gid >= tg.ngroups) break;
     const int count = __ldg(p.cl.count + gid);
     if (count < 0) continue;  // left to the fused kernel
+    const int scan = gid / tg.groups_per_scan;
+    const int tile0 = (gid - scan * tg.groups_per_scan) * kGroupTiles;
+    const int nt = ::min(kGroupTiles, tg.tiles_per_scan - tile0);
     const int world = p.scan_world ? p.scan_world[scan] : (p.scan0 + scan) % p.nworld;
     const WideChild* wslots = p.wslots + (size_t)world * p.nslot;
     const GeomPose* pose = p.pose + (size_t)world * p.ngeom;
+    const CandRef* list = p.cl.list + (size_t)gid * kCandCap;
     double o[3];
 #pragma unroll
     for (int k = 0; k < 3; k++) o[k] = __ldg(p.spos + (size_t)scan * 3 + k);
-    const GroupGen<MODE> gen{p, tg, scan, ti, lane};
-    const GroupEpi<MODE, SPLIT> epi{p, tg, scan, ti, lane};
-    drain_tile(p, wslots, p.elim, pose, 0, o, tcap, warp, gen, epi, count,
-               p.cl.list + (size_t)gid * kCandCap);
-    }
+    const GroupGen<MODE> gen{p, tg, scan, tile0, lane};
+    const GroupEpi<MODE, SPLIT> epi{p, tg, scan, tile0, lane};
+#if B2_DRAIN_STAGED
+    __syncwarp();  // the previous group's tiles are done with ca / cb
+    stage_candidates(warp, wslots, count, list, ca, cb);
+    __syncwarp();
+#endif
+#pragma unroll 1
+    for (int t = 0; t < nt; t++)
+      drain_tile<B2_DRAIN_STAGED != 0>(p, wslots, p.elim, pose, t, o, tcap, warp, gen, epi, count, list,
+                                        ca, cb);
   }
 }
 

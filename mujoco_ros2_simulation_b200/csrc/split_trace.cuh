@@ -169,12 +169,37 @@ B2_HD int collect_group(const CastParams& p, const WideChild* wslots, const Wide
   return nc;
 }
 
+// Copies a group's candidates (list entry + the slot's box, geom id and type) to the warp's shared
+// arrays, one candidate per lane.  All lanes call it; the caller syncs the warp before and after.
+template <class W>
+B2_HD void stage_candidates(W& warp, const WideChild* wslots, int count, const CandRef* list, F4* ca,
+                            F4* cb) {
+  for (int i = warp.lane(); i < count; i += warp.size()) {
+    const CandRef c = ld_cand(list + i);
+    const WideChild ch = ld_wslot<false>(wslots + c.slot);
+    F4 a, b;
+    a.x = ch.lo[0];
+    a.y = ch.lo[1];
+    a.z = ch.lo[2];
+    a.w = c.key2;
+    b.x = ch.hi[0];
+    b.y = ch.hi[1];
+    b.z = ch.hi[2];
+    b.w = int_as_f32((~ch.link) | (ch.pad << 24));
+    ca[i] = a;
+    cb[i] = b;
+  }
+}
+
 // One tile of a group whose candidate list is list[0..count).  wslots: the world's child slots in
 // GLOBAL memory.  Every lane of the warp must call drain_tile together.
-template <class W, class Gen, class Epi>
+//   STAGED: the group's candidates were copied to shared memory by stage_candidates (ca/cb, the
+//   fused kernel's layout: lo.xyz + key2, hi.xyz + geom id | type << 24); else list + wslots are read.
+template <bool STAGED, class W, class Gen, class Epi>
 B2_HD void drain_tile(const CastParams& p, const WideChild* wslots, const uint8_t* elim,
                       const GeomPose* pose, int t, const double pnt[3], float tcap, W& warp,
-                      const Gen& gen, const Epi& epi, int count, const CandRef* list) {
+                      const Gen& gen, const Epi& epi, int count, const CandRef* list,
+                      const F4* ca, const F4* cb) {
   double vec[3];
   int r = -1;
   const bool active = gen(t, vec, r);
@@ -197,14 +222,32 @@ B2_HD void drain_tile(const CastParams& p, const WideChild* wslots, const uint8_
     float tmaxf = hit_tmax(hit, tcap);
     float lim2 = lane_lim2(hit, tcap, vlen_up);
     for (int i = 0; i < count; i++) {
-      const CandRef c = ld_cand(list + i);
-      const bool need = active && c.key2 <= lim2;
+      float key2, lo[3], hi[3];
+      int32_t geom, type;
+      if (STAGED) {
+        const F4 a = ca[i], b = cb[i];
+        key2 = a.w;
+        lo[0] = a.x, lo[1] = a.y, lo[2] = a.z;
+        hi[0] = b.x, hi[1] = b.y, hi[2] = b.z;
+        const int32_t gt = f32_as_int(b.w);
+        geom = gt & 0xffffff;
+        type = gt >> 24;
+      } else {
+        const CandRef c = ld_cand(list + i);
+        key2 = c.key2;
+        if (!warp.any(active && key2 <= lim2)) break;
+        const WideChild ch = ld_wslot<false>(wslots + c.slot);
+        lo[0] = ch.lo[0], lo[1] = ch.lo[1], lo[2] = ch.lo[2];
+        hi[0] = ch.hi[0], hi[1] = ch.hi[1], hi[2] = ch.hi[2];
+        geom = ~ch.link;
+        type = ch.pad;
+      }
+      const bool need = active && key2 <= lim2;
       if (!warp.any(need)) break;  // sorted: nobody can improve on a later candidate either
-      const WideChild ch = ld_wslot<false>(wslots + c.slot);
       float tn = 0.f;
-      const bool h = need && slab_test(rf, ch.lo, ch.hi, tmaxf, tn);
+      const bool h = need && slab_test(rf, lo, hi, tmaxf, tn);
       if (!warp.any(h)) continue;
-      leaf_visit(p, pose, ~ch.link, ch.pad, h, hit, pnt, vec, tcap, warp);
+      leaf_visit(p, pose, geom, type, h, hit, pnt, vec, tcap, warp);
       tmaxf = hit_tmax(hit, tcap);
       lim2 = lane_lim2(hit, tcap, vlen_up);
     }

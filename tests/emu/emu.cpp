@@ -181,8 +181,17 @@ void run(const EmuScene& S, CastParams& p, const double o[3], const double* R) {
       const int n = collect_group<false>(p, p.wslots, p.wnodes, p.elim, p.pose, nt, o, tcap, warp,
                                          gen, list);
       if (n >= 0) {
-        for (int t = 0; t < nt; t++)
-          drain_tile(p, p.wslots, p.elim, p.pose, t, o, tcap, warp, gen, epi, n, list);
+        // staged (the device's default) and unstaged candidate access, alternating per group
+        const bool staged = ((r0 / kGroupTiles) & 1) == 0;
+        if (staged) stage_candidates(warp, p.wslots, n, list, warp.cand_a(), warp.cand_b());
+        for (int t = 0; t < nt; t++) {
+          if (staged)
+            drain_tile<true>(p, p.wslots, p.elim, p.pose, t, o, tcap, warp, gen, epi, n, list,
+                             warp.cand_a(), warp.cand_b());
+          else
+            drain_tile<false>(p, p.wslots, p.elim, p.pose, t, o, tcap, warp, gen, epi, n, list,
+                              nullptr, nullptr);
+        }
         continue;
       }
       g_emu_fallbacks++;
