@@ -543,8 +543,8 @@ def run_b200(args):
 
     # ---- roofline of the dominant kernel (K2 cast) ------------------------------------------------------
     st = scene.stats()
-    # GeomStatic 32 + GeomPose 96 per geom, 32 per BVH child slot, 64 per mesh node, 48 per triangle
-    scene_bytes = cs.model.ngeom * (32 + 96) + st["bvh_nodes"] * 32 + st["mesh_nodes"] * 64 + st["mesh_tris"] * 48
+    # GeomStatic 32 + GeomPose 96 per geom, 32 per BVH child slot, 128 per fanout-4 mesh node, 48 per triangle
+    scene_bytes = cs.model.ngeom * (32 + 96) + st["bvh_nodes"] * 32 + st["mesh_nodes"] * 128 + st["mesh_tris"] * 48
     alg_bytes = BYTES_PER_RAY * rays_per_step + scene_bytes
     peak, how = measured_peak()
     achieved = alg_bytes / (ms_kernel * 1e-3) / 1e9
@@ -584,7 +584,7 @@ def run_b200(args):
                 "bvh_nodes": st["bvh_nodes"], "mesh_nodes": st["mesh_nodes"],
             },
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": traffic, "kernel": "cast_kernel<LIDAR> (+ its mesh-pair kernels: one b2_lidar_cast_device)",
+                         "frac": achieved / peak, "traffic": traffic, "kernel": "K2 cast = collect_kernel -> drain_kernel -> mesh-pair kernels (one b2_lidar_cast_device; drain_kernel is the largest at ~50 %)",
                          "kernel_ms": ms_kernel, "algorithmic_bytes_per_launch": alg_bytes,
                          "peak_source": how,
                          "note": "ray casting is traversal/FP64-issue bound, not HBM bound (SURVEY.md M3)"},
