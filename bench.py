@@ -486,6 +486,25 @@ def run_b200(args):
     d2h = es * nray * BYTES_PER_RAY
     e2e_ok = bool((h_geomid[0].numpy() == geomid[0].cpu().numpy()).all()) if es > 0 else True
 
+    # the same call returning what MujocoLidar::update publishes -- the LaserScan ranges only, 4 B/ray
+    # (ref:src/mujoco_lidar.cpp:256-279; geomid is not part of the message)
+    def e2e_scan_step():
+        engine._capi.check(lib.b2_scene_update_poses(scene._h, 0, 1, h_xpos.data_ptr(), h_xmat.data_ptr()))
+        engine._capi.check(lib.b2_lidar_cast(lidar._h, es, h_world.data_ptr(), h_pos.data_ptr(),
+                                             h_mat.data_ptr(), h_ranges.data_ptr(), None, None, None))
+
+    e2e_scan_step()
+    torch.cuda.synchronize()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        e2e_scan_step()
+    torch.cuda.synchronize()
+    t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_scan_val = world * es * nray * args.steps / float(t.item()) / 1e9
+
     # ---- optional: gather of the results over NVLink (not on the data path) -------------------------
     gather_ms = None
     if args.gather and world > 1:
@@ -590,7 +609,10 @@ def run_b200(args):
                          "note": "ray casting is traversal/FP64-issue bound, not HBM bound (SURVEY.md M3)"},
             "cpu_baseline": cpu,
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "scans_per_step": es, "pinned_numa_node": near.node},
+                    "scans_per_step": es, "pinned_numa_node": near.node,
+                    "outputs": "ranges f32 + geomid i32 (8 B/ray over PCIe)",
+                    "laserscan_only": {"value": e2e_scan_val, "unit": UNIT, "d2h_bytes_per_step": es * nray * 4,
+                                       "outputs": "ranges f32 only, as MujocoLidar::update publishes"}},
             "gpu_launches": int(launches),
             "clocks": clk.summary(),
             "secondary": secondary,
