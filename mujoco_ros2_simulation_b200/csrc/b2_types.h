@@ -3,8 +3,8 @@
 // HBM layout of the scene mirror (DESIGN.md "Data layout"):
 //   GeomStatic  [G]        static per model      32 B  size (f64x3), type, dataid
 //   GeomPose    [W][G]     per world, per step   96 B  xpos (f64x3) + xmat (f64x9), 16-B aligned
-//   BvhNode     [W][N]     geom BVH per world    64 B  both children's fp32 boxes + child links
-//   BvhNode     [sum Nm]   per-mesh triangle BVH 64 B  mesh-local frame, static
+//   WideChild   [W][S]     geom BVH child slots  32 B  fp32 box + link + geom type (fanout-32 tree)
+//   MeshNode4   [sum Nm]   per-mesh triangle BVH 128 B four children's boxes, mesh-local, static
 //   MeshTri     [sum T]    triangles in leaf order 48 B  three float4 (xyz + pad)
 #ifndef B2_TYPES_H
 #define B2_TYPES_H

@@ -1,17 +1,21 @@
 // cast_kernels.cu -- K2: the ray-cast kernels (sm_100a).
 //
-//   K2  cast_kernel        one warp per tile of 32 rays: planes, warp-cooperative collect over the
-//                          fanout-32 geom BVH (tile_trace.cuh), closed-form fp64 primitive tests,
-//                          fused LaserScan / multiRay / GL-depth epilogue.  Mesh geoms are not
-//                          traced here: each (ray, mesh geom) whose box the ray enters becomes a
-//                          PAIR in a compacted global list (SPLIT = true).
-//   K2b mesh_pairs_kernel  one thread per pair: mj_rayMesh through the per-mesh triangle BVH;
-//                          adjacent pairs come from the same tile and the same mesh, so warps are
-//                          full and coherent.  Distances merge with a 64-bit atomicMin.
-//   K2c mesh_ids_kernel    lowest mesh geom id among the pairs that reached the minimum.
-//   K2d mesh_final_kernel  re-runs the epilogue for the rays a mesh changed.
-//   Launches too small to amortise four kernels, and chunks whose pair list overflowed, use
-//   cast_kernel<SPLIT = false>, which traces meshes in place (same results, slower).
+//   K2a collect_kernel     one warp per group of 4 tiles x 32 rays: planes, bounding cone, ONE
+//                          warp-cooperative pass over the fanout-32 geom BVH, sorted candidate list
+//                          to global memory (split_trace.cuh collect_group).
+//   K2b drain_kernel       persistent, one group per fetch: per tile the candidates nearest first --
+//                          fp32 slab test, closed-form fp64 leaf test of the warp-uniform geom type --
+//                          and the fused LaserScan / multiRay / GL-depth epilogue (drain_tile).
+//                          Mesh geoms are not traced here: each (ray, mesh geom) whose box the ray
+//                          enters becomes a PAIR in a compacted global list (SPLIT = true).
+//       fallback_kernel    the groups K2a could not finish in one pass: fused trace_group.
+//   K2  cast_kernel        the fused form (tile_trace.cuh trace_group: collect -> drain -> continue):
+//                          launches below 65 536 rays, scenes without a geom BVH, and the clean-up
+//                          pass that recomputes a chunk in place when the pair list overflowed.
+//   K2c mesh_pairs_kernel  one thread per pair: mj_rayMesh through the mesh's fanout-4 tree,
+//                          persistent while-while with refill; distances merge with a 64-bit atomicMin.
+//   K2d mesh_ids_kernel    lowest mesh geom id among the pairs that reached the minimum.
+//   K2e mesh_final_kernel  re-runs the epilogue for the rays a mesh changed.
 //
 // Compile with -fmad=false: distances must be bit-identical to the CPU oracle (ray_core.cuh).
 // No tensor cores: nothing here is a dense contraction.
