@@ -147,6 +147,10 @@ struct b2_lidar {
   DevBuf<int32_t> d_world, d_geomid;
   DevBuf<float> d_ranges, d_xyz;
   cudaEvent_t chunk_done[2] = {nullptr, nullptr};
+  // cast time of the previous blocking call (events around its kernels): decides how finely the
+  // next one is pipelined against the read-back
+  cudaEvent_t cast_t0 = nullptr, cast_t1 = nullptr;
+  double cast_ns_per_ray = 0.0;
 };
 
 struct b2_camera {
@@ -671,6 +675,8 @@ int b2_lidar_create(b2_scene* s, const b2_lidar_desc* d, b2_lidar** out) {
     e = cudaMemcpy(l->d_elim.ptr, elim.data(), elim.size(), cudaMemcpyHostToDevice);
   for (int i = 0; i < 2 && e == cudaSuccess; i++)
     e = cudaEventCreateWithFlags(&l->chunk_done[i], cudaEventDisableTiming);
+  if (e == cudaSuccess) e = cudaEventCreate(&l->cast_t0);
+  if (e == cudaSuccess) e = cudaEventCreate(&l->cast_t1);
   if (e != cudaSuccess) {
     b2_lidar_destroy(l);
     return fail(B2_ERR_CUDA, std::string("b2_lidar_create: ") + cudaGetErrorString(e));
@@ -695,6 +701,8 @@ int b2_lidar_destroy(b2_lidar* l) {
   l->d_xyz.release();
   for (int i = 0; i < 2; i++)
     if (l->chunk_done[i]) cudaEventDestroy(l->chunk_done[i]);
+  if (l->cast_t0) cudaEventDestroy(l->cast_t0);
+  if (l->cast_t1) cudaEventDestroy(l->cast_t1);
   delete l;
   return B2_OK;
 }
@@ -767,9 +775,15 @@ int b2_lidar_cast(b2_lidar* l, int32_t nscan, const int32_t* scan_world, const d
                             cudaMemcpyHostToDevice, s->stream));
   // pipeline: cast chunk k on the compute stream while chunk k-1 drains over PCIe on the copy
   // stream (the result read-back is 8 B/ray and would otherwise serialise behind the kernel)
-  // 4 / 8 / 16 / 32 chunks measured 5.81 / 6.07 / 6.30 / 5.84 Grays/s end to end (the 54.8 GB/s link
-  // alone allows 6.85 at 8 B/ray)
-  int nchunk = env_int("B2_E2E_CHUNKS", 16);
+  // How many chunks: when the read-back is the longer leg it should start early and never wait
+  // (16 chunks: 6.3 of the 6.85 Grays/s the 54.8 GB/s link allows at 8 B/ray; 4 / 8 / 32 chunks gave
+  // 5.8 / 6.1 / 5.8); when the cast is the longer leg every extra chunk only adds launch tails
+  // (ranges only, 4 B/ray: 4 / 8 / 16 chunks gave 8.0 / 7.8 / 7.2).  The cast time per ray is known
+  // from the previous call on this lidar; the link is taken as 50 GB/s.
+  const double out_bytes = (ranges ? 4.0 : 0.0) + (geomid ? 4.0 : 0.0) + (dist ? 8.0 : 0.0) + (xyz ? 12.0 : 0.0);
+  const double copy_ns_per_ray = out_bytes / 50.0;
+  const double cast_ns_per_ray = l->cast_ns_per_ray > 0 ? l->cast_ns_per_ray : 0.12;
+  int nchunk = env_int("B2_E2E_CHUNKS", copy_ns_per_ray > cast_ns_per_ray ? 16 : 4);
   if (nchunk > nscan) nchunk = nscan;
   if (nchunk < 1) nchunk = 1;
   // equal chunks, except that the first and the last one are cut into quarters: nothing overlaps
@@ -787,6 +801,7 @@ int b2_lidar_cast(b2_lidar* l, int32_t nscan, const int32_t* scan_world, const d
     }
   }
   bounds.push_back(nscan);
+  B2_CUDA(cudaEventRecord(l->cast_t0, s->stream));
   for (size_t c = 0; c + 1 < bounds.size(); c++) {
     const int s0 = bounds[c], s1 = bounds[c + 1];
     const int ns = s1 - s0;
@@ -813,8 +828,12 @@ int b2_lidar_cast(b2_lidar* l, int32_t nscan, const int32_t* scan_world, const d
       B2_CUDA(cudaMemcpyAsync(xyz + 3 * off, l->d_xyz.ptr + 3 * off, cnt * 3 * sizeof(float),
                               cudaMemcpyDeviceToHost, s->copy_stream));
   }
+  B2_CUDA(cudaEventRecord(l->cast_t1, s->stream));
   B2_CUDA(cudaStreamSynchronize(s->stream));
   B2_CUDA(cudaStreamSynchronize(s->copy_stream));
+  float cast_ms = 0.f;
+  if (cudaEventElapsedTime(&cast_ms, l->cast_t0, l->cast_t1) == cudaSuccess && cast_ms > 0.f)
+    l->cast_ns_per_ray = (double)cast_ms * 1e6 / (double)n;
   return B2_OK;
 }
 
