@@ -42,7 +42,7 @@ size_t cast_stage_bytes(int nslot, int nwnode, int ngeom) {
 
 // per-warp shared-memory scratch of the cast kernel
 struct WarpScratch {
-  F4 cand_a[kCandCap];       // candidate box lo.xyz + distance key
+  F4 cand_a[kCandA];         // candidate box lo.xyz + distance key
   F4 cand_b[kCandCap];       // candidate box hi.xyz + geom id bits
   RayState st[kGroupTiles * 32];  // per-ray state of the group between the phases
   int32_t queue[kQueueCap];  // collect frontier
@@ -285,7 +285,7 @@ __global__ void __launch_bounds__(kCastThreads, B2_CAST_MINBLOCKS)
 #endif
 
 struct CollectScratch {
-  F4 cand_a[kCandCap];  // unit directions of the group's rays while the cone is built
+  F4 cand_a[kCandA];  // unit directions of the group's rays while the cone is built
   CandRef cref[kCandCap];
   int32_t queue[kQueueCap];
   int32_t order[kCandCap];

@@ -26,7 +26,12 @@
 namespace b2 {
 
 constexpr int kMaxWideDepth = 5;  // queue: every round pops 1 node and pushes <= 32
-constexpr int kGroupTiles = 4;    // tiles per collect
+#ifndef B2_GROUP_TILES
+#define B2_GROUP_TILES 4
+#endif
+constexpr int kGroupTiles = B2_GROUP_TILES;  // tiles per collect
+// cand_a doubles as the buffer of the group's unit directions (3 floats per ray) while the cone is built
+constexpr int kCandA = kCandCap > kGroupTiles * 24 ? kCandCap : kGroupTiles * 24;
 
 struct B2_ALIGN(16) RayState {
   double vec[3];  // the ray direction (generated once, in phase A)
