@@ -577,6 +577,7 @@ def run_b200(args):
 
     # ---- CPU baseline (rank 0, N=1): the oracle on a bounded sample of the same workload -------------------
     cpu = None
+    parity = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         from oracle import binding as orc
         orc.build()
@@ -586,6 +587,20 @@ def run_b200(args):
         cpu = {"value": rays / secs / 1e9, "unit": UNIT, "cores": cores, "kind": "port",
                "sample": f"{args.cpu_baseline_scans} of the {nscan} scans ({rays} rays), oracle "
                          "(C restatement of mj_multiRay, -O3) on all host cores"}
+        # the same oracle on one thread (what the reference's physics thread has)
+        r1, s1 = cpu_arm(cs, 4, 1, 90)
+        cpu["single_thread"] = {"value": r1 / s1 / 1e9, "unit": UNIT, "sample": f"4 scans ({r1} rays)"}
+        # parity of THIS run's GPU output against the oracle on sampled scans of the timed batch
+        oc = orc.OracleScene(cs.model, cs.poses)
+        g_host, r_host = geomid.cpu().numpy(), ranges.cpu().numpy()
+        checked = bad_id = bad_rng = 0
+        for sc in sorted({0, nscan // 3, nscan - 1}):
+            rr, gg, _ = oc.lidar_scan(cs.lidar, pos[sc], mat[sc], nthread=cores)
+            checked += rr.size
+            bad_id += int((gg != g_host[sc]).sum())
+            bad_rng += int((rr != r_host[sc]).sum())
+        parity = {"rays_checked": checked, "geomid_mismatch": bad_id, "range_bits_mismatch": bad_rng,
+                  "against": "CPU oracle (oracle/), same poses; ranges compared bit for bit"}
 
     if rank == 0:
         line = {
@@ -608,6 +623,7 @@ def run_b200(args):
                          "peak_source": how,
                          "note": "ray casting is traversal/FP64-issue bound, not HBM bound (SURVEY.md M3)"},
             "cpu_baseline": cpu,
+            "parity": parity,
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "scans_per_step": es, "pinned_numa_node": near.node,
                     "outputs": "ranges f32 + geomid i32 (8 B/ray over PCIe)",
