@@ -10,7 +10,7 @@
 //                          enters becomes a PAIR in a compacted global list (SPLIT = true).
 //       fallback_kernel    the groups K2a could not finish in one pass: fused trace_group.
 //   K2  cast_kernel        the fused form (tile_trace.cuh trace_group: collect -> drain -> continue):
-//                          launches below 65 536 rays, scenes without a geom BVH, and the clean-up
+//                          launches below ~1 M rays, scenes without a geom BVH, and the clean-up
 //                          pass that recomputes a chunk in place when the pair list overflowed.
 //   K2c mesh_pairs_kernel  one thread per pair: mj_rayMesh through the mesh's fanout-4 tree,
 //                          persistent while-while with refill; distances merge with a 64-bit atomicMin.
@@ -208,6 +208,8 @@ __global__ void __launch_bounds__(kCastThreads, B2_CAST_MINBLOCKS)
   if (ONLY_IF_OVERFLOW) {
     if (p.ms.counters[2] == 0) return;
   }
+  // dynamic == 2: the fall-back of the two-kernel cast -- only the groups K2a listed (often none)
+  if (tg.dynamic == 2 && p.cl.counters[0] == 0) return;
   WarpScratch* scratch = reinterpret_cast<WarpScratch*>(smem_raw);
   unsigned char* s_stage = smem_raw + kCastWarps * sizeof(WarpScratch);
 
@@ -249,9 +251,16 @@ __global__ void __launch_bounds__(kCastThreads, B2_CAST_MINBLOCKS)
     int scan, tile0, nt;
     if (tg.dynamic) {
       int g = 0;
-      if (lane == 0) g = atomicAdd(p.work_counter, 1);
-      g = __shfl_sync(0xffffffffu, g, 0);
-      if (g >= tg.ngroups) break;
+      if (tg.dynamic == 2) {
+        if (lane == 0) g = atomicAdd(p.cl.counters + 2, 1);
+        g = __shfl_sync(0xffffffffu, g, 0);
+        if (g >= p.cl.counters[0]) break;
+        g = p.cl.ovf_list[g];
+      } else {
+        if (lane == 0) g = atomicAdd(p.work_counter, 1);
+        g = __shfl_sync(0xffffffffu, g, 0);
+        if (g >= tg.ngroups) break;
+      }
       scan = g / tg.groups_per_scan;
       tile0 = (g - scan * tg.groups_per_scan) * kGroupTiles;
       nt = ::min(kGroupTiles, tg.tiles_per_scan - tile0);
@@ -706,7 +715,19 @@ static cudaError_t launch_two_kernel(const CastParams& p, const TileGeom& tg, bo
       p, tg);
   err = cudaGetLastError();
   if (err != cudaSuccess) return err;
-  return launch_tile_kernel(fallback_kernel<MODE, SPLIT>, p, tg, (unsigned)sm_count,
+  // the groups K2a gave up on: the fused kernel.  One world: the persistent staged form of
+  // cast_kernel reading its groups from the list; several worlds: unstaged, world per group.
+  if (p.nworld == 1 && stage) {
+    TileGeom tf = tg;
+    tf.dynamic = 2;
+    return launch_tile_kernel(cast_kernel<MODE, true, SPLIT, false>, p, tf,
+                              (unsigned)(sm_count * B2_CAST_MINBLOCKS),
+                              kCastWarps * sizeof(WarpScratch) +
+                                  cast_stage_bytes(p.nslot, p.nwnode, p.ngeom),
+                              stream);
+  }
+  return launch_tile_kernel(fallback_kernel<MODE, SPLIT>, p, tg,
+                            (unsigned)(sm_count * B2_CAST_MINBLOCKS),
                             kCastWarps * sizeof(WarpScratch), stream);
 }
 

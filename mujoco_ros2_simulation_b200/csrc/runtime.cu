@@ -9,6 +9,7 @@
 #include <atomic>
 #include <mutex>
 #include <cmath>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <string>
@@ -301,8 +302,12 @@ int run_cast(b2_scene* s, CastParams p, cudaStream_t stream) {
   // counters[8..11]: the two-kernel cast (CastLists)
   B2_CUDA(s->d_counters.reserve(16));
   p.work_counter = env_int("B2_DYNAMIC", 1) != 0 ? s->d_counters.ptr + 4 : nullptr;
-  // two-kernel cast (K2a collect -> K2b drain): large launches on scenes with a geom BVH
-  const bool two = env_int("B2_TWO_KERNEL", 1) != 0 && s->nwnode > 0 && total >= 65536;
+  // two-kernel cast (K2a collect -> K2b drain): large launches on scenes with a geom BVH.  Below
+  // ~1 M rays a cast is a chain of latencies, not a throughput problem, and the fused kernel's single
+  // launch wins (tools/crossover.py on B200: 64x2048 lidar 0.5 M rays 269 vs 246 us, 1 M 310 vs 329,
+  // 8 M 1057 vs 1415; a coarse 64x256 table breaks even at ~4 M)
+  const bool two = env_int("B2_TWO_KERNEL", 1) != 0 && s->nwnode > 0 &&
+                   total >= env_int("B2_TWO_MIN_RAYS", 1 << 20);
   // measured on B200 (profiles/r01_sweeps.txt): 8M rays/chunk 5.0, 32M 5.4, whole launch 5.6
   // Grays/s -- fewer, longer kernels lose less in launch gaps and tails; scratch is 68 B/ray
   const long long chunk_rays = env_int("B2_CHUNK_MRAYS", 144) * 1000000LL;
@@ -366,6 +371,14 @@ int run_cast(b2_scene* s, CastParams p, cudaStream_t stream) {
     int nl = 0;
     B2_CUDA(launch_cast(p, stage, tpb, s->sm_count, stream, &nl));
     g_launches += nl;
+    if (two && env_int("B2_DEBUG_LISTS", 0) != 0) {
+      // diagnostics only (blocks): how many groups the collect pass handed to the fused fall-back
+      int32_t c[4] = {0, 0, 0, 0};
+      cudaStreamSynchronize(stream);
+      cudaMemcpy(c, p.cl.counters, sizeof(c), cudaMemcpyDeviceToHost);
+      fprintf(stderr, "[b2] two-kernel cast: %d scans x %d rays, %d groups fell back to the fused kernel\n",
+              p.nscan, p.nray, c[0]);
+    }
   }
   return B2_OK;
 }

@@ -156,7 +156,7 @@ def test_two_kernel_vs_fused_with_overflowing_groups(oracle):
     vec[5000:5040] *= 1e-25                           # |vec|^2 underflows float: no culling for that group
     vec[70000:70100] *= 1e22
     pnt = np.array([6.0, 0.5, 0.2])
-    with _env(B2_TWO_KERNEL=1):
+    with _env(B2_TWO_KERNEL=1, B2_TWO_MIN_RAYS=1):    # (the default threshold is 1 M rays)
         d2, g2 = s.multiray(pnt, vec)
     with _env(B2_TWO_KERNEL=0):
         d1, g1 = s.multiray(pnt, vec)
@@ -165,3 +165,42 @@ def test_two_kernel_vs_fused_with_overflowing_groups(oracle):
     od, og = oracle.OracleScene(m, P).multi_ray(pnt, vec[sel], nthread=8)
     assert np.array_equal(od, d2[sel]) and np.array_equal(og, g2[sel])
     assert (g2 >= 0).mean() > 0.2
+
+
+def test_two_kernel_fall_back_in_several_worlds(oracle):
+    """overflowing groups with nworld > 1: the unstaged fall-back kernel picks the world per group."""
+    import torch
+    from mujoco_ros2_simulation_b200.model import GEOM_BOX, GEOM_SPHERE, Model, Poses, random_rotations
+    rng = np.random.default_rng(31)
+    n, W = 300, 3
+    t = rng.choice([GEOM_BOX, GEOM_SPHERE], size=n)
+    m = Model(t, np.zeros(n, int), np.zeros(n, int), -np.ones(n, int), -np.ones(n, int),
+              rng.uniform(0.4, 1.2, size=(n, 3)), np.ones((n, 4)), np.zeros((0, 4)), [0])
+    pos = rng.normal(size=(W, n, 3)) * 0.7                      # three different dense clusters
+    mat = np.stack([random_rotations(rng, n).reshape(n, 9) for _ in range(W)])
+    P = Poses(pos, mat)
+    s = engine.Scene(m, nworld=W)
+    s.update_poses(P)
+    az = np.linspace(0, 2 * np.pi, 4096, endpoint=False)
+    spec = scenes.LidarSpec(np.stack([np.cos(az), np.sin(az), 0.1 * np.sin(5 * az)], 1))
+    lid = engine.Lidar(s, spec)
+    S = 9
+    spos = np.tile([[5.0, 0.3, 0.1]], (S, 1)) + rng.normal(size=(S, 3)) * 0.2
+    smat = np.tile(np.eye(3).reshape(1, 9), (S, 1))
+    sw = (np.arange(S) % W).astype(np.int32)
+    dev = torch.device("cuda", 0)
+    res = []
+    for two in (1, 0):
+        g = torch.full((S, 4096), -7, dtype=torch.int32, device=dev)
+        d = torch.full((S, 4096), -7.0, dtype=torch.float64, device=dev)
+        with _env(B2_TWO_KERNEL=two, B2_TWO_MIN_RAYS=1):
+            lid.cast_device(S, torch.from_numpy(spos).to(dev), torch.from_numpy(smat).to(dev),
+                            torch.from_numpy(sw).to(dev), geomid=g, dist=d)
+        s.sync()
+        res.append((g.cpu().numpy(), d.cpu().numpy()))
+    assert np.array_equal(res[0][0], res[1][0]) and np.array_equal(res[0][1], res[1][1])
+    for sc in (0, 4, 8):
+        o = oracle.OracleScene(m, P, world=int(sw[sc]))
+        r, gg, raw = o.lidar_scan(spec, spos[sc], smat[sc], nthread=8)
+        assert np.array_equal(raw, res[0][1][sc]) and np.array_equal(gg, res[0][0][sc])
+    assert (res[0][0] >= 0).mean() > 0.1
