@@ -161,6 +161,7 @@ struct CastParams {
   const uint8_t* elim;      // [ngeom] ray_eliminate flags for this sensor
   const double* local_dir;  // [nray*3] (lidar table or multiray vec)
   int32_t nray, tile_w, mode;
+  int32_t group_tiles;      // tiles whose rays share one collect: 4, or fewer for coarse sensors (0 = 4)
   double cutoff, range_min, range_max;
   // camera mode
   int32_t cam_w, cam_h;

@@ -156,6 +156,7 @@ struct TileGeom {
   int tiles_per_block, tiles_per_scan, chunks_per_scan, tiles_x;
   // persistent launch (single-world batches): warps fetch tile groups from p.work_counter
   int dynamic, groups_per_scan, ngroups;
+  int group_tiles;  // tiles per group of this sensor (1, 2 or kGroupTiles = 4)
 };
 
 // ray generator of one group: tile t of the group, this lane's ray.  The sensor frame is
@@ -247,7 +248,7 @@ __global__ void __launch_bounds__(kCastThreads, B2_CAST_MINBLOCKS)
   // each warp walks groups of kGroupTiles consecutive tiles of this CTA's chunk
   // (static launch) or, in a persistent launch, whatever group the global work counter hands out
   // next -- no warp waits for the slowest group of its CTA
-  for (int t = warp_id * kGroupTiles;; t += kCastWarps * kGroupTiles) {
+  for (int t = warp_id * tg.group_tiles;; t += kCastWarps * tg.group_tiles) {
     int scan, tile0, nt;
     if (tg.dynamic) {
       int g = 0;
@@ -262,14 +263,14 @@ __global__ void __launch_bounds__(kCastThreads, B2_CAST_MINBLOCKS)
         if (g >= tg.ngroups) break;
       }
       scan = g / tg.groups_per_scan;
-      tile0 = (g - scan * tg.groups_per_scan) * kGroupTiles;
-      nt = ::min(kGroupTiles, tg.tiles_per_scan - tile0);
+      tile0 = (g - scan * tg.groups_per_scan) * tg.group_tiles;
+      nt = ::min(tg.group_tiles, tg.tiles_per_scan - tile0);
     } else {
       if (t >= tg.tiles_per_block) break;
       scan = scan_b;
       tile0 = chunk * tg.tiles_per_block + t;
       if (tile0 >= tg.tiles_per_scan) break;  // warp-uniform
-      nt = ::min(kGroupTiles, ::min(tg.tiles_per_block - t, tg.tiles_per_scan - tile0));
+      nt = ::min(tg.group_tiles, ::min(tg.tiles_per_block - t, tg.tiles_per_scan - tile0));
     }
     double o[3];
 #pragma unroll
@@ -366,7 +367,7 @@ __global__ void __launch_bounds__(kCastThreads, B2_COLLECT_MINBLOCKS)
   CollectWarp warp{scratch + warp_id, lane};
   const float tcap = (MODE == MODE_MULTIRAY) ? f32_up(p.cutoff) : FLT_MAX;
 
-  for (int t = warp_id * kGroupTiles;; t += kCastWarps * kGroupTiles) {
+  for (int t = warp_id * tg.group_tiles;; t += kCastWarps * tg.group_tiles) {
     int scan, tile0, nt;
     if (tg.dynamic) {
       int g = 0;
@@ -374,20 +375,20 @@ __global__ void __launch_bounds__(kCastThreads, B2_COLLECT_MINBLOCKS)
       g = __shfl_sync(0xffffffffu, g, 0);
       if (g >= tg.ngroups) break;
       scan = g / tg.groups_per_scan;
-      tile0 = (g - scan * tg.groups_per_scan) * kGroupTiles;
-      nt = ::min(kGroupTiles, tg.tiles_per_scan - tile0);
+      tile0 = (g - scan * tg.groups_per_scan) * tg.group_tiles;
+      nt = ::min(tg.group_tiles, tg.tiles_per_scan - tile0);
     } else {
       if (t >= tg.tiles_per_block) break;
       scan = scan_b;
       tile0 = chunk * tg.tiles_per_block + t;
       if (tile0 >= tg.tiles_per_scan) break;  // warp-uniform
-      nt = ::min(kGroupTiles, ::min(tg.tiles_per_block - t, tg.tiles_per_scan - tile0));
+      nt = ::min(tg.group_tiles, ::min(tg.tiles_per_block - t, tg.tiles_per_scan - tile0));
     }
     double o[3];
 #pragma unroll
     for (int k = 0; k < 3; k++) o[k] = __ldg(p.spos + (size_t)scan * 3 + k);
     const GroupGen<MODE> gen{p, tg, scan, tile0, lane};
-    const int gid = scan * tg.groups_per_scan + tile0 / kGroupTiles;
+    const int gid = scan * tg.groups_per_scan + tile0 / tg.group_tiles;
     const int n = collect_group<STAGE>(p, wslots, wnodes, elim, pose, nt, o, tcap, warp, gen,
                                        p.cl.list + (size_t)gid * kCandCap);
     if (lane == 0) {
@@ -428,8 +429,8 @@ __global__ void __launch_bounds__(kCastThreads, B2_DRAIN_MINBLOCKS)
     const int count = __ldg(p.cl.count + gid);
     if (count < 0) continue;  // left to the fused kernel
     const int scan = gid / tg.groups_per_scan;
-    const int tile0 = (gid - scan * tg.groups_per_scan) * kGroupTiles;
-    const int nt = ::min(kGroupTiles, tg.tiles_per_scan - tile0);
+    const int tile0 = (gid - scan * tg.groups_per_scan) * tg.group_tiles;
+    const int nt = ::min(tg.group_tiles, tg.tiles_per_scan - tile0);
     const int world = p.scan_world ? p.scan_world[scan] : (p.scan0 + scan) % p.nworld;
     const WideChild* wslots = p.wslots + (size_t)world * p.nslot;
     const GeomPose* pose = p.pose + (size_t)world * p.ngeom;
@@ -469,8 +470,8 @@ __global__ void __launch_bounds__(kCastThreads, B2_CAST_MINBLOCKS)
     if (idx >= novf) break;
     const int gid = p.cl.ovf_list[idx];
     const int scan = gid / tg.groups_per_scan;
-    const int tile0 = (gid - scan * tg.groups_per_scan) * kGroupTiles;
-    const int nt = ::min(kGroupTiles, tg.tiles_per_scan - tile0);
+    const int tile0 = (gid - scan * tg.groups_per_scan) * tg.group_tiles;
+    const int nt = ::min(tg.group_tiles, tg.tiles_per_scan - tile0);
     const int world = p.scan_world ? p.scan_world[scan] : (p.scan0 + scan) % p.nworld;
     double o[3];
 #pragma unroll
@@ -752,7 +753,8 @@ static cudaError_t launch_cast_mode(const CastParams& p, bool stage, int tiles_p
   if (nblocks <= 0) return cudaSuccess;
   if (nblocks > 0x7fffffffLL) return cudaErrorInvalidConfiguration;
   // persistent launch: one resident wave of CTAs whose warps pull groups from the work counter
-  tg.groups_per_scan = (tg.tiles_per_scan + kGroupTiles - 1) / kGroupTiles;
+  tg.group_tiles = (p.group_tiles == 1 || p.group_tiles == 2) ? p.group_tiles : kGroupTiles;
+  tg.groups_per_scan = (tg.tiles_per_scan + tg.group_tiles - 1) / tg.group_tiles;
   const long long ngroups = (long long)p.nscan * tg.groups_per_scan;
   const long long resident = (long long)sm_count * B2_CAST_MINBLOCKS;
   tg.dynamic = p.work_counter != nullptr && stage && p.nworld == 1 && ngroups <= 0x7fffffffLL &&

@@ -140,6 +140,7 @@ struct b2_scene {
 struct b2_lidar {
   b2_scene* scene = nullptr;
   int nray = 0, tile_w = 0;
+  int group_tiles = 4;  // tiles per collect group, chosen from the angular width of the ray table
   double cutoff = 0, range_min = 0, range_max = 1000;
   DevBuf<double> d_local_dir;
   DevBuf<uint8_t> d_elim;
@@ -315,7 +316,8 @@ int run_cast(b2_scene* s, CastParams p, cudaStream_t stream) {
     scans_per_chunk = (int)std::max(1LL, std::min((long long)p.nscan, chunk_rays / p.nray));
   p.cl = CastLists{};
   if (two) {
-    const size_t groups_per_scan = ((size_t)cast_tiles_per_scan(p.nray) + kGroupTiles - 1) / kGroupTiles;
+    const size_t gt = (p.group_tiles == 1 || p.group_tiles == 2) ? (size_t)p.group_tiles : (size_t)kGroupTiles;
+    const size_t groups_per_scan = ((size_t)cast_tiles_per_scan(p.nray) + gt - 1) / gt;
     const size_t ngroup = groups_per_scan * (size_t)scans_per_chunk;
     B2_CUDA(s->d_cl_count.reserve(ngroup));
     B2_CUDA(s->d_cl_ovf.reserve(ngroup));
@@ -663,6 +665,68 @@ int b2_scene_stats(const b2_scene* s, int32_t* n_bvh_nodes, int32_t* n_planes,
 // ---------------------------------------------------------------------------------------------
 // lidar
 // ---------------------------------------------------------------------------------------------
+namespace {
+
+// Tiles per collect group for a ray table: the largest of 4 / 2 / 1 whose groups all fit a cone of
+// half-angle 10 deg.  The 64x2048 table gives 3 deg at 4 tiles per group; a coarse table (64x256:
+// 23 deg at 4) would hand a third of its groups' over-long candidate lists to the fall-back.
+// Measured (tools/coarse_probe.py, 8.4 M rays, Grays/s at 4 / 2 / 1 tiles per group):
+//   64x128: 2.19 / 2.82 / 3.90   64x256: 3.48 / 5.07 / 4.86   64x512: 5.98 / 6.19 / 5.54
+//   64x2048: 7.91 / 7.43 / 6.29.
+// Sampled on up to 64 groups spread over the table, same tile -> ray mapping as the kernels.
+int choose_group_tiles(const double* dir, int nray, int tile_w) {
+  const int forced = env_int("B2_GROUP_TILES_RT", 0);
+  if (forced == 1 || forced == 2 || forced == 4) return forced;
+  if (nray <= 0 || !dir) return kGroupTiles;
+  int tiles_x = 0, tiles = (nray + 31) / 32;
+  if (tile_w > 0 && tile_w % 8 == 0 && nray % tile_w == 0) {
+    const int rows = nray / tile_w;
+    if (rows >= 4 && rows % 4 == 0) {
+      tiles_x = tile_w / 8;
+      tiles = tiles_x * (rows / 4);
+    }
+  }
+  auto ray_of = [&](int tile, int lane) {
+    if (tiles_x > 0) {
+      const int ty = tile / tiles_x, tx = tile - ty * tiles_x;
+      return (ty * 4 + (lane >> 3)) * tile_w + tx * 8 + (lane & 7);
+    }
+    return tile * 32 + lane;
+  };
+  const double cos_limit = std::cos(10.0 * 3.14159265358979323846 / 180.0);
+  for (int gt = kGroupTiles; gt >= 2; gt >>= 1) {
+    const int groups = (tiles + gt - 1) / gt;
+    const int step = std::max(1, groups / 64);
+    bool ok = true;
+    for (int g = 0; g < groups && ok; g += step) {
+      double ax = 0, ay = 0, az = 0;
+      std::vector<double> u;
+      for (int t = g * gt; t < std::min(tiles, (g + 1) * gt); t++)
+        for (int lane = 0; lane < 32; lane++) {
+          const int r = ray_of(t, lane);
+          if (r >= nray) continue;
+          const double x = dir[3 * (size_t)r], y = dir[3 * (size_t)r + 1], z = dir[3 * (size_t)r + 2];
+          const double n = std::sqrt(x * x + y * y + z * z);
+          if (!(n > 0)) continue;
+          u.push_back(x / n), u.push_back(y / n), u.push_back(z / n);
+          ax += x / n, ay += y / n, az += z / n;
+        }
+      const double an = std::sqrt(ax * ax + ay * ay + az * az);
+      if (u.empty()) continue;
+      if (!(an > 1e-9)) {
+        ok = false;
+        break;
+      }
+      for (size_t i = 0; i < u.size() && ok; i += 3)
+        if ((u[i] * ax + u[i + 1] * ay + u[i + 2] * az) / an < cos_limit) ok = false;
+    }
+    if (ok) return gt;
+  }
+  return 1;
+}
+
+}  // namespace
+
 int b2_lidar_create(b2_scene* s, const b2_lidar_desc* d, b2_lidar** out) {
   if (!s || !d || !out) return fail(B2_ERR_INVALID, "b2_lidar_create: null argument");
   *out = nullptr;
@@ -674,6 +738,7 @@ int b2_lidar_create(b2_scene* s, const b2_lidar_desc* d, b2_lidar** out) {
   l->scene = s;
   l->nray = d->nray;
   l->tile_w = d->tile_w;
+  l->group_tiles = choose_group_tiles(d->local_dir, d->nray, d->tile_w);
   l->cutoff = d->cutoff;
   l->range_min = d->range_min;
   l->range_max = d->range_max;
@@ -735,6 +800,7 @@ static int lidar_launch(b2_lidar* l, int32_t nscan, int32_t scan0, const int32_t
   p.local_dir = l->d_local_dir.ptr;
   p.nray = l->nray;
   p.tile_w = l->tile_w;
+  p.group_tiles = l->group_tiles;
   p.mode = MODE_LIDAR;
   p.cutoff = l->cutoff;
   p.range_min = l->range_min;
