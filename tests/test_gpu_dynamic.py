@@ -204,3 +204,26 @@ def test_two_kernel_fall_back_in_several_worlds(oracle):
         r, gg, raw = o.lidar_scan(spec, spos[sc], smat[sc], nthread=8)
         assert np.array_equal(raw, res[0][1][sc]) and np.array_equal(gg, res[0][0][sc])
     assert (res[0][0] >= 0).mean() > 0.1
+
+
+@pytest.mark.parametrize("n_az,nscan", [(128, 136), (256, 4)])
+def test_group_width_follows_the_ray_table(oracle, n_az, nscan):
+    """coarse ray tables get narrower collect groups (runtime.cu choose_group_tiles): 4, 2 and 1
+    tiles per group and the automatic choice give the same bits as the oracle, in the two-kernel cast
+    (1.1 M rays) and in the fused kernel (65 536 rays)."""
+    cs = scenes.clutter500(n_el=64, n_az=n_az)
+    s = engine.Scene(cs.model)
+    s.update_poses(cs.poses)
+    pos, mat = cs.sensor_poses(nscan)
+    outs = []
+    for gt in (0, 4, 2, 1):
+        with _env(B2_GROUP_TILES_RT=gt):
+            lid = engine.Lidar(s, cs.lidar)
+        outs.append(_cast_dev(lid, s, pos, mat))
+    for o in outs[1:]:
+        assert np.array_equal(o[0], outs[0][0]) and np.array_equal(o[1], outs[0][1])
+        assert np.array_equal(o[2], outs[0][2])
+    oc = oracle.OracleScene(cs.model, cs.poses)
+    for sc in (0, nscan - 1):
+        r, g, raw = oc.lidar_scan(cs.lidar, pos[sc], mat[sc], nthread=8)
+        assert np.array_equal(raw, outs[0][1][sc]) and np.array_equal(g, outs[0][0][sc])
