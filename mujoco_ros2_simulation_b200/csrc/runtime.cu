@@ -314,9 +314,19 @@ int run_cast(b2_scene* s, CastParams p, cudaStream_t stream) {
   const long long chunk_rays = env_int("B2_CHUNK_MRAYS", 144) * 1000000LL;
   if (split || two)
     scans_per_chunk = (int)std::max(1LL, std::min((long long)p.nscan, chunk_rays / p.nray));
+  // small launches: fewer tiles per group until every resident warp has a group -- a cast of a few
+  // thousand tiles is a chain of latencies, and 4 tiles per warp in sequence make it 4x longer
+  {
+    int g = (p.group_tiles == 1 || p.group_tiles == 2) ? p.group_tiles : kGroupTiles;
+    const long long tiles = cast_tiles_per_scan(p.nray);
+    const long long resident_warps = (long long)s->sm_count * 2 * (cast_threads_per_block() / 32);
+    if (env_int("B2_SMALL_SPLIT", 1) != 0)
+      while (g > 1 && (long long)p.nscan * ((tiles + g - 1) / g) < resident_warps) g >>= 1;
+    p.group_tiles = g;
+  }
   p.cl = CastLists{};
   if (two) {
-    const size_t gt = (p.group_tiles == 1 || p.group_tiles == 2) ? (size_t)p.group_tiles : (size_t)kGroupTiles;
+    const size_t gt = (size_t)p.group_tiles;
     const size_t groups_per_scan = ((size_t)cast_tiles_per_scan(p.nray) + gt - 1) / gt;
     const size_t ngroup = groups_per_scan * (size_t)scans_per_chunk;
     B2_CUDA(s->d_cl_count.reserve(ngroup));
@@ -674,10 +684,13 @@ namespace {
 //   64x128: 2.19 / 2.82 / 3.90   64x256: 3.48 / 5.07 / 4.86   64x512: 5.98 / 6.19 / 5.54
 //   64x2048: 7.91 / 7.43 / 6.29.
 // Sampled on up to 64 groups spread over the table, same tile -> ray mapping as the kernels.
-int choose_group_tiles(const double* dir, int nray, int tile_w) {
+int choose_group_tiles(const double* dir, int nray, int tile_w, size_t bvh_geoms) {
   const int forced = env_int("B2_GROUP_TILES_RT", 0);
   if (forced == 1 || forced == 2 || forced == 4) return forced;
   if (nray <= 0 || !dir) return kGroupTiles;
+  // a scene of a few geoms has nothing to cull: narrower groups would only repeat the collect
+  // (4096 arm worlds x 1024-ray planar lidar: 24.5 Grays/s at 4 tiles per group, 17.7 at 1)
+  if (bvh_geoms <= 64) return kGroupTiles;
   int tiles_x = 0, tiles = (nray + 31) / 32;
   if (tile_w > 0 && tile_w % 8 == 0 && nray % tile_w == 0) {
     const int rows = nray / tile_w;
@@ -738,7 +751,7 @@ int b2_lidar_create(b2_scene* s, const b2_lidar_desc* d, b2_lidar** out) {
   l->scene = s;
   l->nray = d->nray;
   l->tile_w = d->tile_w;
-  l->group_tiles = choose_group_tiles(d->local_dir, d->nray, d->tile_w);
+  l->group_tiles = choose_group_tiles(d->local_dir, d->nray, d->tile_w, s->hm.bvh_geoms.size());
   l->cutoff = d->cutoff;
   l->range_min = d->range_min;
   l->range_max = d->range_max;

@@ -10,7 +10,7 @@ cs = scenes.clutter500(n_el=64, n_az=N_AZ)          # 64 x N_AZ rays per scan
 s = engine.Scene(cs.model); s.update_poses(cs.poses)
 dev = torch.device("cuda", 0)
 R = 64 * N_AZ
-for nray_scan, nscan in ((R, 1), (R, 2), (R, 4), (R, 8), (R, 16), (R, 32), (R, 64)):
+for nray_scan, nscan in ((R, 1), (R, 2), (R, 4), (R, 8)):
     spec = scenes.LidarSpec(cs.lidar.local_dir[:nray_scan], tile_w=N_AZ, bodyexclude=63)
     lid = engine.Lidar(s, spec)
     pos, mat = cs.sensor_poses(nscan)
@@ -18,8 +18,8 @@ for nray_scan, nscan in ((R, 1), (R, 2), (R, 4), (R, 8), (R, 16), (R, 32), (R, 6
     r = torch.empty((nscan, nray_scan), dtype=torch.float32, device=dev)
     g = torch.empty((nscan, nray_scan), dtype=torch.int32, device=dev)
     row = [f"{nscan * nray_scan:8d} rays"]
-    for two, split in ((0, 0), (0, 1), (1, 1)):
-        os.environ["B2_TWO_KERNEL"] = str(two); os.environ["B2_TWO_MIN_RAYS"] = "1"; os.environ["B2_SPLIT"] = str(split)
+    for two, split, small in ((0, 1, 0), (0, 1, 1), (1, 1, 1)):
+        os.environ["B2_TWO_KERNEL"] = str(two); os.environ["B2_TWO_MIN_RAYS"] = "1"; os.environ["B2_SPLIT"] = str(split); os.environ["B2_SMALL_SPLIT"] = str(small)
         for _ in range(5):
             lid.cast_device(nscan, dp, dm, None, ranges=r, geomid=g)
         s.sync()
@@ -29,5 +29,5 @@ for nray_scan, nscan in ((R, 1), (R, 2), (R, 4), (R, 8), (R, 16), (R, 32), (R, 6
         for _ in range(20):
             lid.cast_device(nscan, dp, dm, None, ranges=r, geomid=g)
         s.sync(); b.record(); torch.cuda.synchronize()
-        row.append(f"two={two} split={split}: {a.elapsed_time(b) / 20 * 1e3:8.1f} us")
+        row.append(f"two={two} small_split={small}: {a.elapsed_time(b) / 20 * 1e3:8.1f} us")
     print("  ".join(row))
