@@ -31,7 +31,9 @@ namespace b2 {
 #endif
 // heavy leaf routines: one out-of-line copy on the device keeps the kernel's hot loops inside the
 // instruction cache (the fully inlined first version was 140 KB of SASS and stalled on fetch)
-#if defined(__CUDACC__)
+#if defined(__CUDACC__) && defined(B2_INLINE_LEAF)
+#define B2_LEAF static __host__ __device__ __forceinline__
+#elif defined(__CUDACC__)
 #define B2_LEAF static __host__ __device__ __noinline__
 #else
 #define B2_LEAF static inline
