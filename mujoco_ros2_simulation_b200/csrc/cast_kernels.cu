@@ -489,10 +489,11 @@ __global__ void __launch_bounds__(kCastThreads, B2_CAST_MINBLOCKS)
 //
 // Persistent "while-while" traversal (Aila & Laine style): every lane owns one pair at a time and
 // refills itself from a global work counter when its pair is finished, so lanes with short
-// traversals do not idle behind long ones.  Each outer round runs (1) refill, (2) inner nodes until
-// the lane reaches a leaf, (3) the fp64 triangle tests of that leaf -- so the expensive triangle
-// code runs with most lanes active instead of whenever a single lane happens to hit a leaf.
-// The pair already passed mj_rayMesh's box pre-test in K2, so no post-test is needed here.
+// traversals do not idle behind long ones.  Each outer round runs (1) refill, (2) up to six nodes
+// of the mesh's fanout-4 tree per lane, stopping at a leaf, (3) the fp64 triangle tests of the lanes
+// that stand on a leaf -- so the expensive triangle code runs with many lanes active instead of
+// whenever a single lane happens to hit a leaf.
+// The pair already passed mj_rayMesh's box pre-test in K2b, so no post-test is needed here.
 #ifndef B2_MESH_MINBLOCKS
 // CTAs/SM (register cap): 4 / 5 / 6 measured 5.44 / 5.50 / 5.47 Grays/s early on; later, with the
 // kernel bound by node-fetch latency, 5 / 6 / 8 / 10 gave 6.57 / 6.52 / 6.64 / 6.57 (64 regs, 32 warps)

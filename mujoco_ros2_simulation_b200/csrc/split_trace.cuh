@@ -12,9 +12,9 @@
 //                         slab test, warp-uniform fp64 leaf test) and the fused epilogue -- all
 //                         per-ray state stays in registers, no shared memory at all.
 // A group the single pass cannot finish (candidate list full, rays outside the float range) is
-// reported as -1 and traced by the fused trace_group instead: same results, by construction,
-// because K2b visits a superset-free, identically ordered candidate list (the first pass of
-// trace_group with the same cone and the same far bound).
+// reported as -1 and traced by the fused trace_group instead.  Results do not depend on which path
+// a group takes: the list K2b walks is exactly the candidate list of trace_group's first pass (same
+// cone, same far bound, same order), and every accepted distance comes from the same double test.
 #ifndef B2_SPLIT_TRACE_CUH
 #define B2_SPLIT_TRACE_CUH
 
