@@ -390,6 +390,10 @@ int run_cast(b2_scene* s, CastParams p, cudaStream_t stream) {
       cudaMemcpy(c, p.cl.counters, sizeof(c), cudaMemcpyDeviceToHost);
       fprintf(stderr, "[b2] two-kernel cast: %d scans x %d rays, %d groups fell back to the fused kernel\n",
               p.nscan, p.nray, c[0]);
+      if (p.ms.counters) {
+        cudaMemcpy(c, p.ms.counters, sizeof(c), cudaMemcpyDeviceToHost);
+        fprintf(stderr, "[b2] split mesh path: %d (ray, mesh) pairs on %d rays, overflow %d\n", c[0], c[1], c[2]);
+      }
     }
   }
   return B2_OK;

@@ -227,3 +227,27 @@ def test_group_width_follows_the_ray_table(oracle, n_az, nscan):
     for sc in (0, nscan - 1):
         r, g, raw = oc.lidar_scan(cs.lidar, pos[sc], mat[sc], nthread=8)
         assert np.array_equal(raw, outs[0][1][sc]) and np.array_equal(g, outs[0][0][sc])
+
+
+def test_many_tiny_scans(oracle):
+    """50 000 poses of the reference fixture's 24-ray lidar in one call (1.2 M rays, one ragged tile
+    per scan, one group per scan): two-kernel == fused == oracle."""
+    rs = scenes.robot_scene()
+    s = engine.Scene(rs.model)
+    s.update_poses(rs.poses)
+    lid = engine.Lidar(s, rs.lidar)
+    S = 50_000
+    rng = np.random.default_rng(2)
+    pos = rs.lidar_pos[None] + rng.normal(size=(S, 3)) * 0.3
+    mat = np.tile(rs.lidar_mat.reshape(1, 9), (S, 1))
+    with _env(B2_TWO_KERNEL=1, B2_TWO_MIN_RAYS=1):
+        two = _cast_dev(lid, s, pos, mat)
+    with _env(B2_TWO_KERNEL=0):
+        fused = _cast_dev(lid, s, pos, mat)
+    for a, b in zip(two[:3], fused[:3]):
+        assert np.array_equal(a, b, equal_nan=True)
+    assert (two[0] != -7).all()
+    o = oracle.OracleScene(rs.model, rs.poses)
+    for sc in (0, 777, S - 1):
+        r, g, raw = o.lidar_scan(rs.lidar, pos[sc], mat[sc])
+        assert np.array_equal(raw, two[1][sc]) and np.array_equal(g, two[0][sc]) and np.array_equal(r, two[2][sc])
