@@ -16,6 +16,9 @@
  *   - "_device" entry points take device pointers, enqueue on the scene's stream and return
  *     without blocking; the plain entry points take HOST pointers, stage through pinned memory
  *     and block until the result is in the caller's buffer;
+ *   - threads: one scene may be used from several threads at once (the plugin's physics, lidar
+ *     and camera threads do): work on a scene is serialised internally.  A lidar or camera handle
+ *     belongs to one thread at a time, like the wrapper object that owns it;
  *   - there is NO CPU fallback: every entry point fails with B2_ERR_CUDA when no sm_100 device
  *     is usable.
  *   - mjModel / mjData field names are kept so a binding is `desc.geom_type = m->geom_type;`.
