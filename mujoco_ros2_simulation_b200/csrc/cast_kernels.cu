@@ -797,7 +797,8 @@ static cudaError_t launch_cast_mode(const CastParams& p, bool stage, int tiles_p
   }
   if (err != cudaSuccess) return err;
   const unsigned mgrid = (unsigned)(sm_count * 16);
-  mesh_pairs_kernel<MODE><<<mgrid, kMeshThreads, 0, stream>>>(p);
+  // persistent: exactly the CTAs that are resident at once
+  mesh_pairs_kernel<MODE><<<(unsigned)(sm_count * B2_MESH_MINBLOCKS), kMeshThreads, 0, stream>>>(p);
   mesh_ids_kernel<<<mgrid, kMeshThreads, 0, stream>>>(p);
   mesh_final_kernel<MODE><<<mgrid, kMeshThreads, 0, stream>>>(p);
   err = cudaGetLastError();
