@@ -189,6 +189,26 @@ int b2_camera_render_to_cloud(b2_camera* cam, int32_t ncam, const int32_t* cam_w
  * colour buffers that already live on the device (e.g. CUDA-GL interop).  [ncam*H*W*3] bytes. */
 int b2_rgb_flip_device(b2_camera* cam, int32_t ncam, const uint8_t* d_rgb_gl, uint8_t* d_rgb_out);
 
+/* ---- multi-GPU: result gather over NVLink -----------------------
+ * [NOT IN REFERENCE: the reference is a single process on one CPU.]  One process per GPU; worlds /
+ * sensor-pose batches are sharded, nothing is exchanged while casting.  The gather is fused into
+ * the cast: the owner of the gathered array creates a PEER BUFFER (device memory other processes
+ * can map) and publishes its 64-byte handle; every other rank opens the handle and passes
+ * `peer_ptr + its own offset` as the ranges / geomid / depth output of the `_device` entry points.
+ * The kernels' own result stores (128-B float4 / int4 lines) then travel over NVLink / NVSwitch
+ * while the traversal runs -- no staging copy and no separate collective.  The writer must
+ * b2_scene_sync() (or order a stream event) before the owner reads; ordering between processes
+ * is the caller's (one barrier per step). */
+#define B2_PEER_HANDLE_BYTES 64
+/* allocate `bytes` of device memory on `device` and export its handle */
+int b2_peer_buffer_create(int32_t device, size_t bytes, void** d_ptr,
+                          uint8_t handle[B2_PEER_HANDLE_BYTES]);
+/* map another process's buffer into this process (current device = `device`); fails with
+ * B2_ERR_CUDA when the two GPUs are not P2P-connected or the handle is stale */
+int b2_peer_buffer_open(int32_t device, const uint8_t handle[B2_PEER_HANDLE_BYTES], void** d_ptr);
+int b2_peer_buffer_close(int32_t device, void* d_ptr);   /* a pointer from _open  */
+int b2_peer_buffer_destroy(int32_t device, void* d_ptr); /* a pointer from _create */
+
 /* ---- introspection used by bench.py / tests ------------------------------------------------ */
 /* number of kernels this library has launched in this process (all scenes / cameras) */
 long long b2_launch_count(void);

@@ -21,6 +21,9 @@
 // No tensor cores: nothing here is a dense contraction.
 #include <cuda_runtime.h>
 
+#include <cstdint>
+#include <cstdlib>
+
 #include "kernels.cuh"
 #include "ray_core.cuh"
 
@@ -157,6 +160,10 @@ struct TileGeom {
   // persistent launch (single-world batches): warps fetch tile groups from p.work_counter
   int dynamic, groups_per_scan, ngroups;
   int group_tiles;  // tiles per group of this sensor (1, 2 or kGroupTiles = 4)
+  // K2b writes a group's LaserScan results as float4 / int4 (one 128-B line per scan-line segment):
+  // 3-D sensors whose groups are 4 tiles of one tile row, ranges / geomid the only outputs, 16-B
+  // aligned (decided at launch)
+  int vec_out;
 };
 
 // ray generator of one group: tile t of the group, this lane's ray.  The sensor frame is
@@ -177,11 +184,17 @@ struct GroupGen {
 };
 
 // result sink of one group: the split path's affected record, then the fused epilogue
+// K2b with vec_out: s_rng / s_id point at the warp's shared-memory patch and the tile's LaserScan
+// results go there (tile-major, [tile][scan line][8 azimuths]) instead of to global memory; the warp
+// writes the whole 32 x 4 patch after its fourth tile (store_patch).
 template <int MODE, bool SPLIT>
 struct GroupEpi {
   const CastParams& p;
   const TileGeom& tg;
   int scan, tile0, lane;
+  float* s_rng = nullptr;    // [128], or nullptr: write to global memory
+  int32_t* s_id = nullptr;   // [128]
+  int t = 0;                 // tile of the group being drained (vec_out)
   __device__ __forceinline__ void operator()(int r, const Hit& hit, int slot) const {
     if (SPLIT && slot >= 0 && slot < p.ms.aff_cap) {
       const unsigned long long bits =
@@ -192,6 +205,13 @@ struct GroupEpi {
       p.ms.aff_prim_id[slot] = hit.id;
       p.ms.aff_mesh_id[slot] = INT32_MAX;
     }
+    if (MODE == MODE_LIDAR && s_rng != nullptr) {
+      double val;
+      bool filtered;
+      s_rng[t * 32 + lane] = lidar_range(p, hit.dist, val, filtered);
+      s_id[t * 32 + lane] = hit.id;
+      return;
+    }
     double le[3] = {0.0, 0.0, 0.0};
     if (MODE == MODE_LIDAR && p.xyz != nullptr) {
 #pragma unroll
@@ -200,6 +220,22 @@ struct GroupEpi {
     cast_epilogue(p, MODE, scan, r, hit, le);
   }
 };
+
+// the 32 x 4 patch of a group (4 tiles of 8 x 4 rays side by side): lane = (scan line, quad of 4
+// azimuths) reads its quad from the tile that holds it and writes one float4 + one int4 -- each
+// scan-line segment of the patch is one full 128-B line per output array
+__device__ __forceinline__ void store_patch(const CastParams& p, const TileGeom& tg, int scan,
+                                            int tile0, int lane, const float* s_rng,
+                                            const int32_t* s_id) {
+  const int line = lane >> 3, q = lane & 7;
+  const int src = (q >> 1) * 32 + line * 8 + (q & 1) * 4;
+  const int ty = tile0 / tg.tiles_x, tx0 = tile0 - ty * tg.tiles_x;
+  const size_t idx = (size_t)scan * p.nray + (size_t)(ty * 4 + line) * p.tile_w + tx0 * 8 + q * 4;
+  if (p.ranges)
+    *reinterpret_cast<float4*>(p.ranges + idx) = *reinterpret_cast<const float4*>(s_rng + src);
+  if (p.geomid)
+    *reinterpret_cast<int4*>(p.geomid + idx) = *reinterpret_cast<const int4*>(s_id + src);
+}
 
 // ONLY_IF_OVERFLOW: the clean-up launch -- exits at once unless the split pass overflowed
 template <int MODE, bool STAGE, bool SPLIT, bool ONLY_IF_OVERFLOW>
@@ -419,6 +455,11 @@ __global__ void __launch_bounds__(kCastThreads, B2_DRAIN_MINBLOCKS)
   F4* cb = nullptr;
 #endif
   const int lane = threadIdx.x & 31;
+  // result patch of the group a warp is draining (vec_out): 128 ranges + 128 geom ids
+  __shared__ __align__(16) float s_rng[kCastWarps][kGroupTiles * 32];
+  __shared__ __align__(16) int32_t s_id[kCastWarps][kGroupTiles * 32];
+  float* my_rng = s_rng[threadIdx.x >> 5];
+  int32_t* my_id = s_id[threadIdx.x >> 5];
   DevWarp<SPLIT> warp{nullptr, lane, -1};
   const float tcap = (MODE == MODE_MULTIRAY) ? f32_up(p.cutoff) : FLT_MAX;
   for (;;) {
@@ -439,16 +480,28 @@ __global__ void __launch_bounds__(kCastThreads, B2_DRAIN_MINBLOCKS)
 #pragma unroll
     for (int k = 0; k < 3; k++) o[k] = __ldg(p.spos + (size_t)scan * 3 + k);
     const GroupGen<MODE> gen{p, tg, scan, tile0, lane};
-    const GroupEpi<MODE, SPLIT> epi{p, tg, scan, tile0, lane};
+    GroupEpi<MODE, SPLIT> epi{p, tg, scan, tile0, lane};
 #if B2_DRAIN_STAGED
     __syncwarp();  // the previous group's tiles are done with ca / cb
     stage_candidates(warp, wslots, count, list, ca, cb);
     __syncwarp();
 #endif
+    const bool vec = MODE == MODE_LIDAR && tg.vec_out && nt == kGroupTiles;
+    if (vec) {
+      epi.s_rng = my_rng;
+      epi.s_id = my_id;
+    }
 #pragma unroll 1
-    for (int t = 0; t < nt; t++)
+    for (int t = 0; t < nt; t++) {
+      epi.t = t;
       drain_tile<B2_DRAIN_STAGED != 0>(p, wslots, p.elim, pose, t, o, tcap, warp, gen, epi, count, list,
                                         ca, cb);
+    }
+    if (vec) {
+      __syncwarp();
+      store_patch(p, tg, scan, tile0, lane, my_rng, my_id);
+      __syncwarp();  // the patch is reused by this warp's next group
+    }
   }
 }
 
@@ -733,6 +786,12 @@ static cudaError_t launch_two_kernel(const CastParams& p, const TileGeom& tg, bo
                             kCastWarps * sizeof(WarpScratch), stream);
 }
 
+// B2_VEC_OUT=0 turns the float4 / int4 result stores of K2b off (A/B runs)
+static bool env_flag_vec_out() {
+  const char* v = std::getenv("B2_VEC_OUT");
+  return !(v && v[0] == '0');
+}
+
 template <int MODE>
 static cudaError_t launch_cast_mode(const CastParams& p, bool stage, int tiles_per_block,
                                     int sm_count, cudaStream_t stream, int* nlaunch) {
@@ -761,6 +820,10 @@ static cudaError_t launch_cast_mode(const CastParams& p, bool stage, int tiles_p
   tg.dynamic = p.work_counter != nullptr && stage && p.nworld == 1 && ngroups <= 0x7fffffffLL &&
                ngroups >= 4 * resident * kCastWarps;
   tg.ngroups = (int)ngroups;
+  tg.vec_out = env_flag_vec_out() && MODE == MODE_LIDAR && tg.tiles_x > 0 && tg.tiles_x % kGroupTiles == 0 &&
+               tg.group_tiles == kGroupTiles && p.dist == nullptr && p.xyz == nullptr &&
+               (reinterpret_cast<uintptr_t>(p.ranges) & 15) == 0 &&
+               (reinterpret_cast<uintptr_t>(p.geomid) & 15) == 0 && p.nray % 4 == 0;
   const long long nblocks_static = nblocks;
   if (tg.dynamic) nblocks = resident;
   size_t smem = kCastWarps * sizeof(WarpScratch);

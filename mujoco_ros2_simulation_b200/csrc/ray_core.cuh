@@ -265,14 +265,58 @@ B2_HD double ray_quad(double a, double b, double c, double& x0, double& x1) {
   return -1;
 }
 
+// ray_quad's RETURN VALUE only (callers that never look at the second root): the same operations in
+// the same order, but the second division is paid only when the first root is negative.
+B2_HD double ray_quad_first(double a, double b, double c) {
+  double det = b * b - a * c;
+  if (det < kMinVal) return -1;
+  det = sqrt(det);
+  const double x0 = (-b - det) / a;
+  if (x0 >= 0) return x0;
+  const double x1 = (-b + det) / a;
+  if (x1 >= 0) return x1;
+  return -1;
+}
+
 B2_HD double ray_sphere(const double pos[3], double dist_sqr, const double pnt[3],
                         const double vec[3]) {
   const double d0 = pnt[0] - pos[0], d1 = pnt[1] - pos[1], d2 = pnt[2] - pos[2];
   const double a = vec[0] * vec[0] + vec[1] * vec[1] + vec[2] * vec[2];
   const double b = vec[0] * d0 + vec[1] * d1 + vec[2] * d2;
   const double c = d0 * d0 + d1 * d1 + d2 * d2 - dist_sqr;
-  double x0, x1;
-  return ray_quad(a, b, c, x0, x1);
+  return ray_quad_first(a, b, c);
+}
+
+// true iff ray_sphere(pos, dist_sqr, pnt, vec) < 0 -- the bounding-sphere pre-test of capsule /
+// cylinder / box (and of mj_rayMesh's box) only looks at the sign.  a, b, c, det are computed as
+// ray_sphere computes them; the square root and the two divisions are skipped when the sign is
+// certain.  With a > 0 and s = sqrt(det) > 0 the roots x0 = (-b - s)/a <= x1 = (-b + s)/a are both
+// negative iff s < b, and a quotient has the sign of its numerator (it cannot round to -0 while
+// a < 1e290 and |numerator| >= 1e-20, which s >= sqrt(mjMINVAL) guarantees below):
+//   b <= 0                   : x1 >= 0, a hit;
+//   det < b*b * (1 - 1e-12)  : s < b even after the roundings of b*b, sqrt (each <= 2^-53), a miss;
+//   det > b*b * (1 + 1e-12)  : s > b, a hit;
+//   anything else (incl. non-finite or huge operands): the upstream arithmetic as written.
+B2_HD bool sphere_miss(const double pos[3], double dist_sqr, const double pnt[3],
+                       const double vec[3]) {
+  const double d0 = pnt[0] - pos[0], d1 = pnt[1] - pos[1], d2 = pnt[2] - pos[2];
+  const double a = vec[0] * vec[0] + vec[1] * vec[1] + vec[2] * vec[2];
+  const double b = vec[0] * d0 + vec[1] * d1 + vec[2] * d2;
+  const double c = d0 * d0 + d1 * d1 + d2 * d2 - dist_sqr;
+  const double bb = b * b;
+  double det = bb - a * c;
+  if (det < kMinVal) return true;
+#ifndef B2_NO_SIGN_PRETEST
+  if (a < 1e290 && det < 1e290 && fabs(b) < 1e140) {
+    if (b <= 0) return false;
+    if (det < bb * (1.0 - 1e-12)) return true;
+    if (det > bb * (1.0 + 1e-12)) return false;
+  }
+#endif
+  det = sqrt(det);
+  const double x0 = (-b - det) / a;
+  const double x1 = (-b + det) / a;
+  return !(x0 >= 0) && !(x1 >= 0);
 }
 
 B2_HD void keep_min(double& x, double sol) {
@@ -298,7 +342,7 @@ B2_HD double local_capsule(const double size[3], const double lpnt[3], const dou
   double a = lvec[0] * lvec[0] + lvec[1] * lvec[1];
   double b = lvec[0] * lpnt[0] + lvec[1] * lpnt[1];
   double c = lpnt[0] * lpnt[0] + lpnt[1] * lpnt[1] - sq_size0;
-  const double sol = ray_quad(a, b, c, x0, x1);
+  const double sol = ray_quad_first(a, b, c);
   if (sol >= 0 && fabs(lpnt[2] + sol * lvec[2]) <= size[1]) keep_min(x, sol);
   a += lvec[2] * lvec[2];
   // caps: side = +1 top (accept z >= size1), side = -1 bottom (accept z <= -size1)
@@ -321,8 +365,7 @@ B2_HD double local_ellipsoid(const double size[3], const double lpnt[3], const d
   const double a = s0 * lvec[0] * lvec[0] + s1 * lvec[1] * lvec[1] + s2 * lvec[2] * lvec[2];
   const double b = s0 * lvec[0] * lpnt[0] + s1 * lvec[1] * lpnt[1] + s2 * lvec[2] * lpnt[2];
   const double c = s0 * lpnt[0] * lpnt[0] + s1 * lpnt[1] * lpnt[1] + s2 * lpnt[2] * lpnt[2] - 1;
-  double x0, x1;
-  return ray_quad(a, b, c, x0, x1);
+  return ray_quad_first(a, b, c);
 }
 
 B2_HD double local_cylinder(const double size[3], const double lpnt[3], const double lvec[3]) {
@@ -341,8 +384,7 @@ B2_HD double local_cylinder(const double size[3], const double lpnt[3], const do
   const double a = lvec[0] * lvec[0] + lvec[1] * lvec[1];
   const double b = lvec[0] * lpnt[0] + lvec[1] * lpnt[1];
   const double c = lpnt[0] * lpnt[0] + lpnt[1] * lpnt[1] - size[0] * size[0];
-  double x0, x1;
-  const double sol = ray_quad(a, b, c, x0, x1);
+  const double sol = ray_quad_first(a, b, c);
   if (sol >= 0 && fabs(lpnt[2] + sol * lvec[2]) <= size[1]) keep_min(x, sol);
   return x;
 }
@@ -394,11 +436,44 @@ B2_HD double local_box(const double size[3], const double lpnt[3], const double 
   return x;
 }
 
+// a pose is fetched in two steps so that a test which ends at the bounding-sphere pre-test (or is a
+// sphere) never touches the rotation: pos + mat[0] (two 16-B loads), then mat[1..8] (four)
+B2_HD void ld_pose_head(const GeomPose* ptr, double pos[3], double& m0) {
+#if B2_ON_DEVICE
+  const double2* q = reinterpret_cast<const double2*>(ptr);
+  const double2 a = __ldg(q), b = __ldg(q + 1);
+  pos[0] = a.x;
+  pos[1] = a.y;
+  pos[2] = b.x;
+  m0 = b.y;
+#else
+  pos[0] = ptr->pos[0];
+  pos[1] = ptr->pos[1];
+  pos[2] = ptr->pos[2];
+  m0 = ptr->mat[0];
+#endif
+}
+B2_HD void ld_pose_tail(const GeomPose* ptr, double m0, double mat[9]) {
+  mat[0] = m0;
+#if B2_ON_DEVICE
+  const double2* q = reinterpret_cast<const double2*>(ptr);
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    const double2 v = __ldg(q + 2 + i);
+    mat[1 + 2 * i] = v.x;
+    mat[2 + 2 * i] = v.y;
+  }
+#else
+  for (int i = 1; i < 9; i++) mat[i] = ptr->mat[i];
+#endif
+}
+
 // mju_rayGeom for one primitive geom (also the geom_size box of a mesh geom when type = GEOM_BOX
 // is forced by the caller).  Out of line on the device: one copy serves every call site.
 B2_LEAF double prim_test(int type, const GeomPose* gp, const GeomStatic* gsp, double px, double py,
                          double pz, double vx, double vy, double vz) {
-  const GeomPose P = ld_pose(gp);
+  GeomPose P;
+  ld_pose_head(gp, P.pos, P.mat[0]);
   const GeomStatic gs = ld_gstat(gsp);
   const double pnt[3] = {px, py, pz}, vec[3] = {vx, vy, vz};
   if (type == GEOM_SPHERE) return ray_sphere(P.pos, gs.size[0] * gs.size[0], pnt, vec);
@@ -413,8 +488,9 @@ B2_LEAF double prim_test(int type, const GeomPose* gp, const GeomStatic* gsp, do
     } else {
       ssz = gs.size[0] * gs.size[0] + gs.size[1] * gs.size[1] + gs.size[2] * gs.size[2];
     }
-    if (ray_sphere(P.pos, ssz, pnt, vec) < 0) return -1;
+    if (sphere_miss(P.pos, ssz, pnt, vec)) return -1;
   }
+  ld_pose_tail(gp, P.mat[0], P.mat);
 #ifndef B2_NO_PLANE_FAST
   if (type == GEOM_PLANE && gs.size[0] <= 0 && gs.size[1] <= 0) {
     // unbounded plane (the usual ground plane, tested for every ray): only the local z components
@@ -774,17 +850,24 @@ B2_HD float quiet_nan() {
 #endif
 }
 
+// engine_sensor.c apply_cutoff, then ref:src/mujoco_lidar.cpp:262 (double -> float) and :269-271
+// (filter on the float against the double limits).  val = the mj_ray value after the cutoff.
+B2_HD float lidar_range(const CastParams& p, double dist, double& val, bool& filtered) {
+  val = dist;
+  if (p.cutoff > 0 && val > p.cutoff) val = p.cutoff;
+  float rng = (float)val;
+  filtered = ((double)rng < p.range_min) || ((double)rng > p.range_max);
+  if (filtered) rng = -1.0f;
+  return rng;
+}
+
 B2_HD void cast_epilogue(const CastParams& p, int mode, int scan, int r, const Hit& hit,
                          const double l[3]) {
   const size_t idx = (size_t)scan * p.nray + r;
   if (mode == MODE_LIDAR) {
-    // engine_sensor.c apply_cutoff, then ref:src/mujoco_lidar.cpp:262 (double -> float) and
-    // :269-271 (filter on the float against the double limits)
-    double val = hit.dist;
-    if (p.cutoff > 0 && val > p.cutoff) val = p.cutoff;
-    float rng = (float)val;
-    const bool filtered = ((double)rng < p.range_min) || ((double)rng > p.range_max);
-    if (filtered) rng = -1.0f;
+    double val;
+    bool filtered;
+    const float rng = lidar_range(p, hit.dist, val, filtered);
     if (p.ranges) p.ranges[idx] = rng;
     if (p.geomid) p.geomid[idx] = hit.id;
     if (p.dist) p.dist[idx] = val;

@@ -1223,4 +1223,64 @@ int b2_camera_render_to_cloud(b2_camera* c, int32_t ncam, const int32_t* cam_wor
   return B2_OK;
 }
 
+// ---------------------------------------------------------------------------------------------
+// multi-GPU: peer buffers (CUDA IPC).  The gather itself is the cast kernels' result stores.
+// ---------------------------------------------------------------------------------------------
+static_assert(sizeof(cudaIpcMemHandle_t) == B2_PEER_HANDLE_BYTES, "handle size");
+
+int b2_peer_buffer_create(int32_t device, size_t bytes, void** d_ptr, uint8_t* handle) {
+  if (!d_ptr || !handle || bytes == 0) return fail(B2_ERR_INVALID, "b2_peer_buffer_create: bad argument");
+  *d_ptr = nullptr;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    cudaGetLastError();
+    return fail(B2_ERR_CUDA, "no CUDA device: this engine has no CPU fallback");
+  }
+  if (device < 0 || device >= ndev) return fail(B2_ERR_INVALID, "device index out of range");
+  B2_CUDA(cudaSetDevice(device));
+  void* p = nullptr;
+  B2_CUDA(cudaMalloc(&p, bytes));
+  cudaIpcMemHandle_t h;
+  cudaError_t e = cudaIpcGetMemHandle(&h, p);
+  if (e != cudaSuccess) {
+    cudaFree(p);
+    return fail(B2_ERR_CUDA, std::string("cudaIpcGetMemHandle: ") + cudaGetErrorString(e));
+  }
+  std::memcpy(handle, &h, sizeof(h));
+  *d_ptr = p;
+  return B2_OK;
+}
+
+int b2_peer_buffer_open(int32_t device, const uint8_t* handle, void** d_ptr) {
+  if (!d_ptr || !handle) return fail(B2_ERR_INVALID, "b2_peer_buffer_open: null argument");
+  *d_ptr = nullptr;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    cudaGetLastError();
+    return fail(B2_ERR_CUDA, "no CUDA device: this engine has no CPU fallback");
+  }
+  if (device < 0 || device >= ndev) return fail(B2_ERR_INVALID, "device index out of range");
+  B2_CUDA(cudaSetDevice(device));
+  cudaIpcMemHandle_t h;
+  std::memcpy(&h, handle, sizeof(h));
+  void* p = nullptr;
+  B2_CUDA(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+  *d_ptr = p;
+  return B2_OK;
+}
+
+int b2_peer_buffer_close(int32_t device, void* d_ptr) {
+  if (!d_ptr) return B2_OK;
+  B2_CUDA(cudaSetDevice(device));
+  B2_CUDA(cudaIpcCloseMemHandle(d_ptr));
+  return B2_OK;
+}
+
+int b2_peer_buffer_destroy(int32_t device, void* d_ptr) {
+  if (!d_ptr) return B2_OK;
+  B2_CUDA(cudaSetDevice(device));
+  B2_CUDA(cudaFree(d_ptr));
+  return B2_OK;
+}
+
 }  // extern "C"

@@ -20,9 +20,11 @@ def _np_ptr(a):
 
 
 def _ptr(x):
-    """void* of a numpy array, a torch tensor (CPU or CUDA) or None."""
+    """void* of a numpy array, a torch tensor (CPU or CUDA), a raw address (int) or None."""
     if x is None:
         return None
+    if isinstance(x, int):  # a raw device pointer (e.g. a slice of a peer buffer, shard.PeerGather.ptr)
+        return C.c_void_p(x)
     if isinstance(x, np.ndarray):
         return C.c_void_p(x.ctypes.data)
     return C.c_void_p(x.data_ptr())

@@ -420,6 +420,41 @@ def clutter_worlds(scene: ClutterScene, nworld: int, seed: int = SEED + 2, step:
     return Poses(xpos, xmat)
 
 
+def clutter_world_block(scene: ClutterScene, world0: int, nworld: int, seed: int = SEED + 5,
+                        step: int = 0) -> Poses:
+    """S5 poses of worlds [world0, world0 + nworld) of a job of any size: world w's body jitter
+    (+-0.5 m, +-20 deg about a random axis; the world body and the sensor body stay put) depends only
+    on (seed, step, w), so a rank's block is the same whether the job runs on 1 or 8 GPUs
+    (shard.world_block).  Vectorised over worlds: 4096 worlds x 503 geoms in about a second."""
+    gb = scene.model.geom_bodyid
+    lpos, lmat = scene.body_of_geom_local
+    nb = scene.body_pos.shape[0]
+    g = scene.model.ngeom
+    dp = np.empty((nworld, nb, 3))
+    ang = np.empty((nworld, nb))
+    ax = np.empty((nworld, nb, 3))
+    for i in range(nworld):
+        rng = np.random.default_rng([seed, step, world0 + i])
+        dp[i] = rng.uniform(-0.5, 0.5, size=(nb, 3))
+        ang[i] = np.deg2rad(rng.uniform(-20, 20, size=nb))
+        ax[i] = rng.normal(size=(nb, 3))
+    for b in (0, nb - 1):
+        dp[:, b] = 0
+        ang[:, b] = 0
+    ax /= np.linalg.norm(ax, axis=2, keepdims=True) + 1e-300
+    # Rodrigues: R = I + sin(a) K + (1 - cos(a)) K^2
+    K = np.zeros((nworld, nb, 3, 3))
+    K[..., 0, 1], K[..., 0, 2] = -ax[..., 2], ax[..., 1]
+    K[..., 1, 0], K[..., 1, 2] = ax[..., 2], -ax[..., 0]
+    K[..., 2, 0], K[..., 2, 1] = -ax[..., 1], ax[..., 0]
+    sa, ca = np.sin(ang)[..., None, None], np.cos(ang)[..., None, None]
+    rb = np.eye(3) + sa * K + (1 - ca) * (K @ K)
+    pb = scene.body_pos[None] + dp
+    xpos = pb[:, gb] + np.einsum("wgij,gj->wgi", rb[:, gb], lpos)
+    xmat = np.einsum("wgij,gjk->wgik", rb[:, gb], lmat).reshape(nworld, g, 9)
+    return Poses(xpos, xmat)
+
+
 # ------------------------------------------------------------------------------------------------
 # S4: GL-style depth buffers
 # ------------------------------------------------------------------------------------------------

@@ -239,6 +239,13 @@ double orc_ray_geom(const double pos[3], const double mat[9], const double size[
   }
 }
 
+void orc_ray_geom_batch(int n, const double* pos, const double* mat, const double* size,
+                        const double* pnt, const double* vec, const int32_t* geomtype, double* out) {
+  for (int i = 0; i < n; i++)
+    out[i] = orc_ray_geom(pos + 3 * (size_t)i, mat + 9 * (size_t)i, size + 3 * (size_t)i,
+                          pnt + 3 * (size_t)i, vec + 3 * (size_t)i, geomtype[i]);
+}
+
 /* ------------------------------------------------------------------------------------------
  * A.4 mesh
  * ---------------------------------------------------------------------------------------- */

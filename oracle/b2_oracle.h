@@ -78,6 +78,9 @@ typedef struct orc_data {
 /* ---- A.3 primitive tests --------------------------------------------------------------- */
 double orc_ray_geom(const double pos[3], const double mat[9], const double size[3],
                     const double pnt[3], const double vec[3], int geomtype);
+/* n independent (geom, ray) cases: arrays [n*3] / [n*9] / [n]; out[n] (test harness convenience) */
+void orc_ray_geom_batch(int n, const double* pos, const double* mat, const double* size,
+                        const double* pnt, const double* vec, const int32_t* geomtype, double* out);
 
 /* ---- A.4 mesh ---------------------------------------------------------------------------- */
 /* number of BVH nodes a mesh with nface faces needs (2*nface-1) */

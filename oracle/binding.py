@@ -57,6 +57,8 @@ def lib():
         L = C.CDLL(_SO)
         L.orc_ray_geom.restype = C.c_double
         L.orc_ray_geom.argtypes = [_f64p, _f64p, _f64p, _f64p, _f64p, C.c_int]
+        L.orc_ray_geom_batch.restype = None
+        L.orc_ray_geom_batch.argtypes = [C.c_int] + [_f64p] * 5 + [_i32p, _f64p]
         L.orc_ray.restype = C.c_double
         L.orc_ray.argtypes = [C.POINTER(_OrcModel), C.POINTER(_OrcData), _f64p, _f64p, _u8p, C.c_uint8,
                               C.c_int, _i32p]
@@ -189,6 +191,15 @@ class OracleScene:
 def ray_geom(pos, mat, size, pnt, vec, geomtype) -> float:
     a = [_c(x, np.float64) for x in (pos, mat, size, pnt, vec)]
     return lib().orc_ray_geom(*[_p(x, _f64p) for x in a], int(geomtype))
+
+
+def ray_geom_batch(pos, mat, size, pnt, vec, geomtype) -> np.ndarray:
+    """n independent (geom, ray) cases through orc_ray_geom: arrays [n,3] / [n,9] / [n]."""
+    a = [_c(x, np.float64) for x in (pos, mat, size, pnt, vec)]
+    t = _c(geomtype, np.int32)
+    out = np.empty(t.size, np.float64)
+    lib().orc_ray_geom_batch(int(t.size), *[_p(x, _f64p) for x in a], _p(t, _i32p), _p(out, _f64p))
+    return out
 
 
 def lidar_num_rangefinders(min_angle, max_angle, inc) -> int:

@@ -260,6 +260,32 @@ int emu_lidar(const b2_model_desc* m, const double* xpos, const double* xmat,
 
 long long emu_fallbacks() { return g_emu_fallbacks; }
 
+// the sign-only bounding-sphere pre-test: out[i] = sphere_miss(pos, r*r, pnt, vec)
+void emu_sphere_miss_batch(int n, const double* pos, const double* radius, const double* pnt,
+                           const double* vec, uint8_t* out) {
+  for (int i = 0; i < n; i++)
+    out[i] = sphere_miss(pos + 3 * (size_t)i, radius[i] * radius[i], pnt + 3 * (size_t)i,
+                         vec + 3 * (size_t)i)
+                 ? 1
+                 : 0;
+}
+
+// n independent (geom, ray) cases through the product's prim_test (the kernels' leaf routine)
+void emu_prim_batch(int n, const double* pos, const double* mat, const double* size,
+                    const double* pnt, const double* vec, const int32_t* type, double* out) {
+  for (int i = 0; i < n; i++) {
+    GeomPose P;
+    GeomStatic gs{};
+    for (int k = 0; k < 3; k++) P.pos[k] = pos[3 * (size_t)i + k];
+    for (int k = 0; k < 9; k++) P.mat[k] = mat[9 * (size_t)i + k];
+    for (int k = 0; k < 3; k++) gs.size[k] = size[3 * (size_t)i + k];
+    gs.type = type[i];
+    const double* o = pnt + 3 * (size_t)i;
+    const double* v = vec + 3 * (size_t)i;
+    out[i] = prim_test(type[i], &P, &gs, o[0], o[1], o[2], v[0], v[1], v[2]);
+  }
+}
+
 // BVH statistics for tests: child slots / depth of the wide geom BVH and total mesh nodes
 int emu_bvh_stats(const b2_model_desc* m, const double* xpos, const double* xmat, int mesh_leaf,
                   int32_t* nslot, int32_t* depth, int64_t* mesh_nodes) {

@@ -48,8 +48,31 @@ def lib():
         L.emu_bvh_stats.restype = C.c_int
         L.emu_bvh_stats.argtypes = [C.POINTER(_capi.ModelDesc), C.c_void_p, C.c_void_p, C.c_int,
                                     C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int64)]
+        L.emu_prim_batch.restype = None
+        L.emu_prim_batch.argtypes = [C.c_int] + [C.c_void_p] * 7
+        L.emu_sphere_miss_batch.restype = None
+        L.emu_sphere_miss_batch.argtypes = [C.c_int] + [C.c_void_p] * 5
         _lib = L
     return _lib
+
+
+def sphere_miss_batch(pos, radius, pnt, vec) -> np.ndarray:
+    """the kernels' sign-only bounding-sphere pre-test (ray_core.cuh sphere_miss) on n cases."""
+    a = [np.ascontiguousarray(x, np.float64) for x in (pos, radius, pnt, vec)]
+    out = np.empty(a[1].size, np.uint8)
+    lib().emu_sphere_miss_batch(int(a[1].size), *[C.c_void_p(x.ctypes.data) for x in a],
+                                C.c_void_p(out.ctypes.data))
+    return out.astype(bool)
+
+
+def prim_batch(pos, mat, size, pnt, vec, geomtype) -> np.ndarray:
+    """n independent (geom, ray) cases through the kernels' leaf routine prim_test."""
+    a = [np.ascontiguousarray(x, np.float64) for x in (pos, mat, size, pnt, vec)]
+    t = np.ascontiguousarray(geomtype, np.int32)
+    out = np.empty(t.size, np.float64)
+    lib().emu_prim_batch(int(t.size), *[C.c_void_p(x.ctypes.data) for x in a],
+                         C.c_void_p(t.ctypes.data), C.c_void_p(out.ctypes.data))
+    return out
 
 
 def _p(a):
