@@ -14,8 +14,9 @@
  *     (thread-local);
  *   - handles are opaque; every output buffer is caller-allocated;
  *   - "_device" entry points take device pointers, enqueue on the scene's stream and return
- *     without blocking; the plain entry points take HOST pointers, stage through pinned memory
- *     and block until the result is in the caller's buffer;
+ *     without blocking; the plain entry points take HOST pointers and block until the result
+ *     is in the caller's buffer: pinned (cudaHostAlloc / cudaHostRegister) buffers are written by
+ *     the copy engine directly, pageable ones through the library's own pinned staging;
  *   - threads: one scene may be used from several threads at once (the plugin's physics, lidar
  *     and camera threads do): work on a scene is serialised internally.  A lidar or camera handle
  *     belongs to one thread at a time, like the wrapper object that owns it;
@@ -101,6 +102,10 @@ typedef struct b2_camera_desc {
   double znear, zfar;    /* vis.map.znear / zfar */
   double extent;         /* stat.extent */
   int32_t point_step;    /* PointCloud2 point_step: 12 (x,y,z) or 16 (x,y,z,pad) */
+  /* geom groups the ray-cast renderer draws (mjvOption.geomgroup).  geomgroup_set == 0: the
+   * reference's mjv_defaultOption (ref:src/mujoco_cameras.cpp:165) = groups 0-2 visible, 3-5 hidden */
+  uint8_t geomgroup[B2_NGROUP];
+  uint8_t geomgroup_set;
 } b2_camera_desc;
 
 /* ---- library ------------------------------------------------------------------------------ */
@@ -111,16 +116,19 @@ const char* b2_last_error(void);
 /* ---- scene mirror --------------------------------------------------------------------------
  * b2_scene_create: called from on_init after LoadModel (ref:src/mujoco_system_interface.cpp:677).
  * Copies the static model, builds the per-mesh triangle BVHs and allocates nworld pose slots.
- * The geom BVH topology is built by the first b2_scene_update_poses covering world 0 and refit
- * on every later update.  stream: a cudaStream_t to enqueue on, or NULL for an internal one. */
+ * The geom BVH topology is built from the first world of the first b2_scene_update_poses (worlds
+ * that update does not cover start as copies of it) and refit on every later update.  stream: a cudaStream_t to enqueue on, or NULL for an internal one. */
 int b2_scene_create(const b2_model_desc* model, int32_t nworld, int32_t device, void* stream,
                     b2_scene** out);
 int b2_scene_destroy(b2_scene* scene);
 
 /* Per-step pose refresh: mjData geom_xpos [nworld*ngeom*3] / geom_xmat [nworld*ngeom*9] for
  * worlds [world0, world0+nworld).  Called by the physics thread right after mj_step
- * (ref:src/mujoco_system_interface.cpp:1691,1731) while it holds sim_mutex_: the host version
- * copies into pinned staging, enqueues the upload and the BVH refit, and returns. */
+ * (ref:src/mujoco_system_interface.cpp:1691,1731) while it holds sim_mutex_.  After the first
+ * update, a host update of ALL worlds only copies into a pinned "latest wins" slot -- no CUDA call,
+ * no scene mutex, never waits for the GPU (microseconds); the next cast / render / sync uploads the
+ * newest slot on a dedicated copy stream and refits before it runs.  Partial-range and device
+ * updates are enqueued at once (upload on the copy stream, refit on the scene's stream). */
 int b2_scene_update_poses(b2_scene* scene, int32_t world0, int32_t nworld,
                           const double* geom_xpos, const double* geom_xmat);
 int b2_scene_update_poses_device(b2_scene* scene, int32_t world0, int32_t nworld,
@@ -148,6 +156,28 @@ int b2_lidar_cast(b2_lidar* lidar, int32_t nscan, const int32_t* scan_world,
 int b2_lidar_cast_device(b2_lidar* lidar, int32_t nscan, const int32_t* d_scan_world,
                          const double* d_sensor_pos, const double* d_sensor_mat, float* d_ranges,
                          int32_t* d_geomid, double* d_dist, float* d_xyz);
+
+/* The blocking call split in two, for callers that sample the sensor frame under their own
+ * simulation mutex (ref:src/mujoco_lidar.cpp:247-250 holds sim_mutex_ while it copies sensordata):
+ * _begin enqueues everything -- pending pose refresh, sensor poses, the cast, the read-back into
+ * pinned staging -- under one hold of the scene mutex and returns without waiting for the GPU, so
+ * calling it with the simulation mutex held pins sensor frame and geom poses to the same step; _end
+ * waits and copies into the buffers given to _begin (which must stay valid).  One cast in flight per
+ * lidar.  Single scans replay a captured CUDA graph from the second call of a shape on. */
+int b2_lidar_cast_begin(b2_lidar* lidar, int32_t nscan, const int32_t* scan_world,
+                        const double* sensor_pos, const double* sensor_mat, float* ranges,
+                        int32_t* geomid, double* dist, float* xyz);
+int b2_lidar_cast_end(b2_lidar* lidar);
+/* ranges + geom ids as uint16 (0xFFFF = miss; needs ngeom < 65535): 6 B/ray over the host link
+ * instead of 8 */
+int b2_lidar_cast_u16(b2_lidar* lidar, int32_t nscan, const int32_t* scan_world,
+                      const double* sensor_pos, const double* sensor_mat, float* ranges,
+                      uint16_t* geomid16);
+int b2_lidar_cast_u16_device(b2_lidar* lidar, int32_t nscan, const int32_t* d_scan_world,
+                             const double* d_sensor_pos, const double* d_sensor_mat,
+                             float* d_ranges, uint16_t* d_geomid16);
+/* device time (us) of the last blocking / begin-end host cast: first enqueue to last kernel */
+double b2_lidar_last_device_us(const b2_lidar* lidar);
 
 /* mj_multiRay-shaped entry (MuJoCo 3.3.4 engine_ray.c) on `world`.
  * Host pointers, blocking.  Hits farther than cutoff are reported as misses. */
@@ -184,6 +214,13 @@ int b2_camera_render_depth_device(b2_camera* cam, int32_t ncam, const int32_t* d
 int b2_camera_render_to_cloud(b2_camera* cam, int32_t ncam, const int32_t* cam_world,
                               const double* cam_pos, const double* cam_mat, float* gl_depth,
                               float* depth32fc1, void* cloud);
+
+/* begin / end form of the above (see b2_lidar_cast_begin): results are staged through pinned
+ * memory, so the output buffers may be pageable (sensor_msgs data vectors) */
+int b2_camera_render_to_cloud_begin(b2_camera* cam, int32_t ncam, const int32_t* cam_world,
+                                    const double* cam_pos, const double* cam_mat, float* gl_depth,
+                                    float* depth32fc1, void* cloud);
+int b2_camera_render_to_cloud_end(b2_camera* cam);
 
 /* N2: RGB8 row flip of ncam images of this camera model (ref:src/mujoco_cameras.cpp:243-249) for
  * colour buffers that already live on the device (e.g. CUDA-GL interop).  [ncam*H*W*3] bytes. */

@@ -41,6 +41,7 @@ class CameraDesc(C.Structure):
     _fields_ = [
         ("width", C.c_int32), ("height", C.c_int32), ("fovy", C.c_double), ("znear", C.c_double),
         ("zfar", C.c_double), ("extent", C.c_double), ("point_step", C.c_int32),
+        ("geomgroup", C.c_uint8 * 6), ("geomgroup_set", C.c_uint8),
     ]
 
 
@@ -64,6 +65,13 @@ SYMBOLS = {
     "b2_lidar_destroy": (C.c_int, [C.c_void_p]),
     "b2_lidar_cast": (C.c_int, [C.c_void_p, C.c_int32] + [C.c_void_p] * 7),
     "b2_lidar_cast_device": (C.c_int, [C.c_void_p, C.c_int32] + [C.c_void_p] * 7),
+    "b2_lidar_cast_begin": (C.c_int, [C.c_void_p, C.c_int32] + [C.c_void_p] * 7),
+    "b2_lidar_cast_end": (C.c_int, [C.c_void_p]),
+    "b2_lidar_cast_u16": (C.c_int, [C.c_void_p, C.c_int32] + [C.c_void_p] * 5),
+    "b2_lidar_cast_u16_device": (C.c_int, [C.c_void_p, C.c_int32] + [C.c_void_p] * 5),
+    "b2_lidar_last_device_us": (C.c_double, [C.c_void_p]),
+    "b2_camera_render_to_cloud_begin": (C.c_int, [C.c_void_p, C.c_int32] + [C.c_void_p] * 6),
+    "b2_camera_render_to_cloud_end": (C.c_int, [C.c_void_p]),
     "b2_multiray": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint8,
                               C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_double]),
     "b2_camera_create": (C.c_int, [C.c_void_p, C.c_int32, C.POINTER(CameraDesc),

@@ -177,6 +177,7 @@ struct CastParams {
   // outputs (nullable)
   float* ranges;
   int32_t* geomid;
+  uint16_t* geomid16;  // compact ids (0xFFFF = miss) for scenes with < 65535 geoms
   double* dist;
   float* xyz;
   float* gl_depth;

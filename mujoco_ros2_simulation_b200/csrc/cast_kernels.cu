@@ -235,6 +235,13 @@ __device__ __forceinline__ void store_patch(const CastParams& p, const TileGeom&
     *reinterpret_cast<float4*>(p.ranges + idx) = *reinterpret_cast<const float4*>(s_rng + src);
   if (p.geomid)
     *reinterpret_cast<int4*>(p.geomid + idx) = *reinterpret_cast<const int4*>(s_id + src);
+  if (p.geomid16) {
+    const int4 v = *reinterpret_cast<const int4*>(s_id + src);
+    uint2 w;
+    w.x = ((uint32_t)v.x & 0xffffu) | ((uint32_t)v.y << 16);
+    w.y = ((uint32_t)v.z & 0xffffu) | ((uint32_t)v.w << 16);
+    *reinterpret_cast<uint2*>(p.geomid16 + idx) = w;
+  }
 }
 
 // ONLY_IF_OVERFLOW: the clean-up launch -- exits at once unless the split pass overflowed
@@ -823,7 +830,8 @@ static cudaError_t launch_cast_mode(const CastParams& p, bool stage, int tiles_p
   tg.vec_out = env_flag_vec_out() && MODE == MODE_LIDAR && tg.tiles_x > 0 && tg.tiles_x % kGroupTiles == 0 &&
                tg.group_tiles == kGroupTiles && p.dist == nullptr && p.xyz == nullptr &&
                (reinterpret_cast<uintptr_t>(p.ranges) & 15) == 0 &&
-               (reinterpret_cast<uintptr_t>(p.geomid) & 15) == 0 && p.nray % 4 == 0;
+               (reinterpret_cast<uintptr_t>(p.geomid) & 15) == 0 &&
+               (reinterpret_cast<uintptr_t>(p.geomid16) & 7) == 0 && p.nray % 4 == 0;
   const long long nblocks_static = nblocks;
   if (tg.dynamic) nblocks = resident;
   size_t smem = kCastWarps * sizeof(WarpScratch);

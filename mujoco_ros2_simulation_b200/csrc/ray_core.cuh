@@ -870,6 +870,7 @@ B2_HD void cast_epilogue(const CastParams& p, int mode, int scan, int r, const H
     const float rng = lidar_range(p, hit.dist, val, filtered);
     if (p.ranges) p.ranges[idx] = rng;
     if (p.geomid) p.geomid[idx] = hit.id;
+    if (p.geomid16) p.geomid16[idx] = (uint16_t)hit.id;  // -1 -> 0xFFFF
     if (p.dist) p.dist[idx] = val;
     if (p.xyz) {
       const bool ok = hit.id >= 0 && !filtered;

@@ -114,11 +114,28 @@ struct b2_scene {
   int nslot = 0, nwnode = 0, nlevel = 0, wide_depth = 0;
   DevBuf<WideNode> d_wnodes;
   DevBuf<int32_t> d_slot_link, d_refit_slots, d_level_start;
-  // pose staging (double-buffered pinned host memory + device raw arrays)
+  // pose staging of the immediate (partial-range) path: double-buffered pinned host memory
   PinBuf<double> h_stage[2];
   cudaEvent_t stage_done[2] = {nullptr, nullptr};
   int stage_flip = 0;
+  // device raw arrays (mjData layout), two halves used alternately; refit_done[f]: the refit that
+  // read half f has finished (the next upload into it waits for that on the copy stream)
   DevBuf<double> d_raw;
+  cudaEvent_t refit_done[2] = {nullptr, nullptr};
+  int raw_flip = 0;
+  // "latest wins" host mirror of mjData's geom poses (full-range updates after the first one): the
+  // producer (physics thread) only copies into a pinned slot -- no CUDA call, no scene mutex; the
+  // next consumer (cast / render / sync) uploads the newest slot on the copy stream and refits.
+  struct PoseMirror {
+    std::mutex idx;   // guards the indices below, never held across a memcpy or a CUDA call
+    std::mutex prod;  // serialises producers
+    PinBuf<double> slot[3];
+    int latest = -1, uploading = -1;
+    unsigned long long version = 0, uploaded = 0;
+    cudaEvent_t upload_done = nullptr;
+    bool upload_pending = false;
+  } pm;
+  int topo_version = 0;  // bumped by every topology (re)build: invalidates captured graphs
   // scratch of the split mesh path (sized for one chunk of rays)
   DevBuf<int32_t> d_pair_slot, d_pair_geom, d_aff_prim_id, d_aff_mesh_id, d_counters;
   DevBuf<double> d_pair_x;
@@ -137,6 +154,29 @@ struct b2_scene {
   DevBuf<uint8_t> d_mr_elim;
 };
 
+// One host cast between b2_lidar_cast_begin and b2_lidar_cast_end
+struct HostCast {
+  bool active = false;
+  bool small = false;   // one piece, linear on the scene's stream (CUDA-graph cached)
+  bool staged = false;  // results land in the lidar's pinned staging first
+  int nscan = 0;
+  size_t n = 0;  // rays
+  float* ranges = nullptr;
+  int32_t* geomid = nullptr;
+  uint16_t* geomid16 = nullptr;
+  double* dist = nullptr;
+  float* xyz = nullptr;
+  std::vector<int> bounds;  // scan bounds of the pieces (bulk path)
+};
+
+struct LidarGraph {
+  int nscan = 0, mask = 0, topo_version = -1;
+  bool has_world = false;
+  bool seen = false;  // the same shape ran once un-captured (all allocations exist)
+  int kernels = 0;    // kernels inside the captured graph (b2_launch_count accounting)
+  cudaGraphExec_t exec = nullptr;
+};
+
 struct b2_lidar {
   b2_scene* scene = nullptr;
   int nray = 0, tile_w = 0;
@@ -147,12 +187,22 @@ struct b2_lidar {
   // scratch of the host-pointer entry point
   DevBuf<double> d_spos, d_smat, d_dist;
   DevBuf<int32_t> d_world, d_geomid;
+  DevBuf<uint16_t> d_geomid16;
   DevBuf<float> d_ranges, d_xyz;
-  cudaEvent_t chunk_done[2] = {nullptr, nullptr};
+  // pinned staging: sensor poses in, results out (when the caller's buffers are pageable, and always
+  // on the small path so that the whole call is one replayable graph over fixed addresses)
+  PinBuf<double> h_in;
+  PinBuf<unsigned char> h_out;
+  size_t off_ranges = 0, off_geomid = 0, off_geomid16 = 0, off_dist = 0, off_xyz = 0;
+  std::vector<cudaEvent_t> piece_done;  // D2H of piece c has landed
+  cudaEvent_t all_done = nullptr;       // everything of the current host cast (small path)
   // cast time of the previous blocking call (events around its kernels): decides how finely the
   // next one is pipelined against the read-back
   cudaEvent_t cast_t0 = nullptr, cast_t1 = nullptr;
   double cast_ns_per_ray = 0.0;
+  double last_device_us = 0.0;  // device time of the last host cast (first enqueue .. last kernel)
+  HostCast pend;
+  LidarGraph graph;
 };
 
 struct b2_camera {
@@ -164,10 +214,24 @@ struct b2_camera {
   double K[9];
   float near_f = 0, far_f = 0, depth_scale = 0;
   DevBuf<float> d_in, d_depth, d_cloud;
-  DevBuf<uint8_t> d_elim;  // no geom eliminated for the ray-cast depth
+  DevBuf<uint8_t> d_elim;  // geoms the renderer does not draw (invisible, hidden groups)
   DevBuf<double> d_pos, d_mat;
   DevBuf<int32_t> d_world;
+  // host render (begin .. end): pinned staging in / out, completion event
+  PinBuf<double> h_in;
+  PinBuf<unsigned char> h_out;
+  cudaEvent_t done = nullptr;
+  struct {
+    bool active = false;
+    int ncam = 0;
+    float* gl_depth = nullptr;
+    float* depth32fc1 = nullptr;
+    void* cloud = nullptr;
+    size_t off_gl = 0, off_depth = 0, off_cloud = 0;
+  } pend;
 };
+
+static int flush_pending(b2_scene* s);  // newest poses of the host mirror -> device (+ refit)
 
 namespace {
 
@@ -226,6 +290,7 @@ int build_topology(b2_scene* s, const double* xpos, const double* xmat) {
     B2_CUDA(cudaStreamSynchronize(s->stream));
   }
   s->topo_built = true;
+  s->topo_version++;
   return B2_OK;
 }
 
@@ -293,6 +358,10 @@ void cast_shape(const b2_scene* s, const CastParams& p, bool& stage, int& tiles_
 int run_cast(b2_scene* s, CastParams p, cudaStream_t stream) {
   if (p.nscan <= 0 || p.nray <= 0) return B2_OK;
   std::lock_guard<std::recursive_mutex> lock(s->mtx);
+  {
+    int rc = flush_pending(s);  // newest poses of the host mirror, if the producer left any
+    if (rc != B2_OK) return rc;
+  }
   const long long total = (long long)p.nscan * p.nray;
   bool split = s->has_mesh_geoms && total >= 65536;
   const int force = env_int("B2_SPLIT", -1);
@@ -373,6 +442,7 @@ int run_cast(b2_scene* s, CastParams p, cudaStream_t stream) {
     p.smat = base.smat ? base.smat + 9 * (size_t)s0 : nullptr;
     p.ranges = base.ranges ? base.ranges + roff : nullptr;
     p.geomid = base.geomid ? base.geomid + roff : nullptr;
+    p.geomid16 = base.geomid16 ? base.geomid16 + roff : nullptr;
     p.dist = base.dist ? base.dist + roff : nullptr;
     p.xyz = base.xyz ? base.xyz + 3 * roff : nullptr;
     p.gl_depth = base.gl_depth ? base.gl_depth + roff : nullptr;
@@ -484,8 +554,11 @@ int b2_scene_create(const b2_model_desc* m, int32_t nworld, int32_t device, void
   if (cudaStreamCreateWithFlags(&s->copy_stream, cudaStreamNonBlocking) != cudaSuccess)
     return cleanup_fail(fail(B2_ERR_CUDA, "cudaStreamCreate failed"));
   for (int i = 0; i < 2; i++)
-    if (cudaEventCreateWithFlags(&s->stage_done[i], cudaEventDisableTiming) != cudaSuccess)
+    if (cudaEventCreateWithFlags(&s->stage_done[i], cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&s->refit_done[i], cudaEventDisableTiming) != cudaSuccess)
       return cleanup_fail(fail(B2_ERR_CUDA, "cudaEventCreate failed"));
+  if (cudaEventCreateWithFlags(&s->pm.upload_done, cudaEventDisableTiming) != cudaSuccess)
+    return cleanup_fail(fail(B2_ERR_CUDA, "cudaEventCreate failed"));
 
   const size_t G = (size_t)m->ngeom;
   HostModel& hm = s->hm;
@@ -572,10 +645,73 @@ int b2_scene_destroy(b2_scene* s) {
   for (int i = 0; i < 2; i++) {
     s->h_stage[i].release();
     if (s->stage_done[i]) cudaEventDestroy(s->stage_done[i]);
+    if (s->refit_done[i]) cudaEventDestroy(s->refit_done[i]);
   }
+  for (int i = 0; i < 3; i++) s->pm.slot[i].release();
+  if (s->pm.upload_done) cudaEventDestroy(s->pm.upload_done);
   if (s->own_stream && s->stream) cudaStreamDestroy(s->stream);
   delete s;
   return B2_OK;
+}
+
+}  // extern "C"
+
+// Upload the newest slot of the "latest wins" host mirror (if any) and refit.  Called by every
+// consumer with the scene mutex held.  H2D rides the copy stream; the refit waits for it on the
+// scene's stream; the upload into a d_raw half waits for the refit that last read that half.
+static int flush_pending(b2_scene* s) {
+  b2_scene::PoseMirror& pm = s->pm;
+  {
+    std::lock_guard<std::mutex> g(pm.idx);
+    if (pm.version == pm.uploaded) return B2_OK;
+  }
+  if (pm.upload_pending) {
+    // the previous upload must have consumed its slot before the slot indices move on
+    B2_CUDA(cudaEventSynchronize(pm.upload_done));
+    pm.upload_pending = false;
+  }
+  int slot;
+  unsigned long long v;
+  {
+    std::lock_guard<std::mutex> g(pm.idx);
+    slot = pm.latest;
+    pm.uploading = slot;
+    v = pm.version;
+  }
+  const size_t G = (size_t)s->ngeom, W = (size_t)s->nworld;
+  const size_t n3 = G * 3 * W, n9 = G * 9 * W, half = G * 12 * W;
+  B2_CUDA(s->d_raw.reserve(2 * half));
+  const int f = s->raw_flip;
+  s->raw_flip ^= 1;
+  double* d_dst = s->d_raw.ptr + (size_t)f * half;
+  B2_CUDA(cudaStreamWaitEvent(s->copy_stream, s->refit_done[f], 0));
+  B2_CUDA(cudaMemcpyAsync(d_dst, pm.slot[slot].ptr, (n3 + n9) * sizeof(double),
+                          cudaMemcpyHostToDevice, s->copy_stream));
+  B2_CUDA(cudaEventRecord(pm.upload_done, s->copy_stream));
+  pm.upload_pending = true;
+  B2_CUDA(cudaStreamWaitEvent(s->stream, pm.upload_done, 0));
+  int rc = run_refit(s, 0, s->nworld, d_dst, d_dst + n3);
+  if (rc != B2_OK) return rc;
+  B2_CUDA(cudaEventRecord(s->refit_done[f], s->stream));
+  pm.uploaded = v;
+  return B2_OK;
+}
+
+// Worlds that have not been updated yet mirror the poses of the world the topology was built on, so
+// that a cast against them walks valid boxes (their results are that world's, not garbage).
+static int seed_all_worlds(b2_scene* s, int src_world) {
+  if (s->nworld <= 1 || s->ngeom == 0) return B2_OK;
+  const size_t G = (size_t)s->ngeom;
+  // world `src_world` first into world 0, then doubling copies
+  if (src_world != 0)
+    B2_CUDA(cudaMemcpyAsync(s->d_pose.ptr, s->d_pose.ptr + G * src_world, G * sizeof(GeomPose),
+                            cudaMemcpyDeviceToDevice, s->stream));
+  for (size_t have = 1; have < (size_t)s->nworld; have *= 2) {
+    const size_t n = std::min(have, (size_t)s->nworld - have);
+    B2_CUDA(cudaMemcpyAsync(s->d_pose.ptr + G * have, s->d_pose.ptr, n * G * sizeof(GeomPose),
+                            cudaMemcpyDeviceToDevice, s->stream));
+  }
+  return run_refit(s, 0, s->nworld, nullptr, nullptr);
 }
 
 static int update_poses_common(b2_scene* s, int32_t world0, int32_t nworld, const double* xpos,
@@ -584,29 +720,61 @@ static int update_poses_common(b2_scene* s, int32_t world0, int32_t nworld, cons
   if (!xpos || !xmat) return fail(B2_ERR_INVALID, "null pose array");
   if (world0 < 0 || nworld < 1 || world0 + nworld > s->nworld)
     return fail(B2_ERR_INVALID, "world range out of bounds");
-  std::lock_guard<std::recursive_mutex> lock(s->mtx);
-  B2_CUDA(cudaSetDevice(s->device));
   if (s->ngeom == 0) return B2_OK;
   const size_t G = (size_t)s->ngeom;
   const size_t n3 = G * 3 * nworld, n9 = G * 9 * nworld;
+
+  // ---- the per-step refresh of the plugin (host arrays, all worlds, topology already built):
+  //      copy into a pinned slot and return -- no CUDA call, no scene mutex, never waits for the GPU
+  if (!on_device && world0 == 0 && nworld == s->nworld && s->topo_built && s->pm.slot[2].ptr) {
+    b2_scene::PoseMirror& pm = s->pm;
+    std::lock_guard<std::mutex> prod(pm.prod);
+    int w = 0;
+    {
+      std::lock_guard<std::mutex> g(pm.idx);
+      while (w == pm.latest || w == pm.uploading) w++;
+    }
+    std::memcpy(pm.slot[w].ptr, xpos, n3 * sizeof(double));
+    std::memcpy(pm.slot[w].ptr + n3, xmat, n9 * sizeof(double));
+    {
+      std::lock_guard<std::mutex> g(pm.idx);
+      pm.latest = w;
+      pm.version++;
+    }
+    return B2_OK;
+  }
+
+  std::lock_guard<std::recursive_mutex> lock(s->mtx);
+  B2_CUDA(cudaSetDevice(s->device));
+  {
+    int rc = flush_pending(s);  // keep the order of updates
+    if (rc != B2_OK) return rc;
+  }
   const double* d_xpos = xpos;
   const double* d_xmat = xmat;
   const double* h_first_pos = xpos;
   const double* h_first_mat = xmat;
   std::vector<double> first;  // first world's poses on the host for the topology build
+  int f = -1;
   if (!on_device) {
-    // pinned double buffer: the caller may reuse its arrays as soon as we return
-    const int f = s->stage_flip;
+    // pinned double buffer: the caller may reuse its arrays as soon as we return.  The upload
+    // rides the copy stream; the refit waits for it on the scene's stream.
+    const int hf = s->stage_flip;
     s->stage_flip ^= 1;
-    B2_CUDA(s->h_stage[f].reserve(n3 + n9));
-    B2_CUDA(cudaEventSynchronize(s->stage_done[f]));
-    std::memcpy(s->h_stage[f].ptr, xpos, n3 * sizeof(double));
-    std::memcpy(s->h_stage[f].ptr + n3, xmat, n9 * sizeof(double));
-    B2_CUDA(s->d_raw.reserve(2 * (G * 12 * (size_t)s->nworld)));
-    double* d_dst = s->d_raw.ptr + (size_t)f * (G * 12 * (size_t)s->nworld);
-    B2_CUDA(cudaMemcpyAsync(d_dst, s->h_stage[f].ptr, (n3 + n9) * sizeof(double),
-                            cudaMemcpyHostToDevice, s->stream));
-    B2_CUDA(cudaEventRecord(s->stage_done[f], s->stream));
+    B2_CUDA(s->h_stage[hf].reserve(n3 + n9));
+    B2_CUDA(cudaEventSynchronize(s->stage_done[hf]));
+    std::memcpy(s->h_stage[hf].ptr, xpos, n3 * sizeof(double));
+    std::memcpy(s->h_stage[hf].ptr + n3, xmat, n9 * sizeof(double));
+    const size_t half = G * 12 * (size_t)s->nworld;
+    B2_CUDA(s->d_raw.reserve(2 * half));
+    f = s->raw_flip;
+    s->raw_flip ^= 1;
+    double* d_dst = s->d_raw.ptr + (size_t)f * half;
+    B2_CUDA(cudaStreamWaitEvent(s->copy_stream, s->refit_done[f], 0));
+    B2_CUDA(cudaMemcpyAsync(d_dst, s->h_stage[hf].ptr, (n3 + n9) * sizeof(double),
+                            cudaMemcpyHostToDevice, s->copy_stream));
+    B2_CUDA(cudaEventRecord(s->stage_done[hf], s->copy_stream));
+    B2_CUDA(cudaStreamWaitEvent(s->stream, s->stage_done[hf], 0));
     d_xpos = d_dst;
     d_xmat = d_dst + n3;
   } else if (!s->topo_built) {
@@ -619,12 +787,33 @@ static int update_poses_common(b2_scene* s, int32_t world0, int32_t nworld, cons
     h_first_pos = first.data();
     h_first_mat = first.data() + G * 3;
   }
-  if (!s->topo_built) {
+  const bool first_update = !s->topo_built;
+  if (first_update) {
     int rc = build_topology(s, h_first_pos, h_first_mat);
     if (rc != B2_OK) return rc;
   }
-  return run_refit(s, world0, nworld, d_xpos, d_xmat);
+  int rc = run_refit(s, world0, nworld, d_xpos, d_xmat);
+  if (rc != B2_OK) return rc;
+  if (f >= 0) B2_CUDA(cudaEventRecord(s->refit_done[f], s->stream));
+  if (first_update) {
+    if (nworld < s->nworld) {
+      rc = seed_all_worlds(s, world0);
+      if (rc != B2_OK) return rc;
+      // the caller's worlds again, on top of the seed
+      rc = run_refit(s, world0, nworld, d_xpos, d_xmat);
+      if (rc != B2_OK) return rc;
+      if (f >= 0) B2_CUDA(cudaEventRecord(s->refit_done[f], s->stream));
+    }
+    // the pinned slots of the "latest wins" mirror, allocated once, outside the per-step path
+    // (bounded: bulk multi-world simulations feed device arrays and never need them)
+    const size_t slot_elems = G * 12 * (size_t)s->nworld;
+    if (!on_device && slot_elems * sizeof(double) <= ((size_t)64 << 20))
+      for (int i = 0; i < 3; i++) B2_CUDA(s->pm.slot[i].reserve(slot_elems));
+  }
+  return B2_OK;
 }
+
+extern "C" {
 
 int b2_scene_update_poses(b2_scene* s, int32_t world0, int32_t nworld, const double* geom_xpos,
                           const double* geom_xmat) {
@@ -643,6 +832,10 @@ int b2_scene_rebuild(b2_scene* s, int32_t world) {
   std::lock_guard<std::recursive_mutex> lock(s->mtx);
   B2_CUDA(cudaSetDevice(s->device));
   if (s->ngeom == 0) return B2_OK;
+  {
+    int rc = flush_pending(s);
+    if (rc != B2_OK) return rc;
+  }
   const size_t G = (size_t)s->ngeom;
   std::vector<GeomPose> hp(G);
   B2_CUDA(cudaMemcpyAsync(hp.data(), s->d_pose.ptr + G * world, G * sizeof(GeomPose),
@@ -661,6 +854,11 @@ int b2_scene_rebuild(b2_scene* s, int32_t world) {
 int b2_scene_sync(b2_scene* s) {
   if (!s) return fail(B2_ERR_INVALID, "null scene");
   B2_CUDA(cudaSetDevice(s->device));
+  {
+    std::lock_guard<std::recursive_mutex> lock(s->mtx);
+    int rc = flush_pending(s);
+    if (rc != B2_OK) return rc;
+  }
   B2_CUDA(cudaStreamSynchronize(s->stream));
   B2_CUDA(cudaStreamSynchronize(s->copy_stream));
   return B2_OK;
@@ -768,8 +966,7 @@ int b2_lidar_create(b2_scene* s, const b2_lidar_desc* d, b2_lidar** out) {
                    cudaMemcpyHostToDevice);
   if (e == cudaSuccess && !elim.empty())
     e = cudaMemcpy(l->d_elim.ptr, elim.data(), elim.size(), cudaMemcpyHostToDevice);
-  for (int i = 0; i < 2 && e == cudaSuccess; i++)
-    e = cudaEventCreateWithFlags(&l->chunk_done[i], cudaEventDisableTiming);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&l->all_done, cudaEventDisableTiming);
   if (e == cudaSuccess) e = cudaEventCreate(&l->cast_t0);
   if (e == cudaSuccess) e = cudaEventCreate(&l->cast_t1);
   if (e != cudaSuccess) {
@@ -794,8 +991,13 @@ int b2_lidar_destroy(b2_lidar* l) {
   l->d_geomid.release();
   l->d_ranges.release();
   l->d_xyz.release();
-  for (int i = 0; i < 2; i++)
-    if (l->chunk_done[i]) cudaEventDestroy(l->chunk_done[i]);
+  l->d_geomid16.release();
+  l->h_in.release();
+  l->h_out.release();
+  for (cudaEvent_t ev : l->piece_done)
+    if (ev) cudaEventDestroy(ev);
+  if (l->all_done) cudaEventDestroy(l->all_done);
+  if (l->graph.exec) cudaGraphExecDestroy(l->graph.exec);
   if (l->cast_t0) cudaEventDestroy(l->cast_t0);
   if (l->cast_t1) cudaEventDestroy(l->cast_t1);
   delete l;
@@ -806,11 +1008,14 @@ int b2_lidar_destroy(b2_lidar* l) {
 // to world (scan0 + s) % nworld)
 static int lidar_launch(b2_lidar* l, int32_t nscan, int32_t scan0, const int32_t* d_world,
                         const double* d_pos, const double* d_mat, float* d_ranges,
-                        int32_t* d_geomid, double* d_dist, float* d_xyz, cudaStream_t stream) {
+                        int32_t* d_geomid, uint16_t* d_geomid16, double* d_dist, float* d_xyz,
+                        cudaStream_t stream) {
   b2_scene* s = l->scene;
   if (nscan == 0 || l->nray == 0) return B2_OK;
   if (s->ngeom > 0 && !s->topo_built)
     return fail(B2_ERR_INVALID, "cast before the first b2_scene_update_poses");
+  if (d_geomid16 && s->ngeom >= 65535)
+    return fail(B2_ERR_INVALID, "uint16 geom ids need a model with fewer than 65535 geoms");
   CastParams p{};
   fill_cast_scene(s, p);
   p.elim = l->d_elim.ptr;
@@ -829,6 +1034,7 @@ static int lidar_launch(b2_lidar* l, int32_t nscan, int32_t scan0, const int32_t
   p.smat = d_mat;
   p.ranges = d_ranges;
   p.geomid = d_geomid;
+  p.geomid16 = d_geomid16;
   p.dist = d_dist;
   p.xyz = d_xyz;
   return run_cast(s, p, stream);
@@ -842,50 +1048,215 @@ int b2_lidar_cast_device(b2_lidar* l, int32_t nscan, const int32_t* d_scan_world
   if (nscan > 0 && (!d_sensor_pos || !d_sensor_mat)) return fail(B2_ERR_INVALID, "null sensor pose");
   B2_CUDA(cudaSetDevice(l->scene->device));
   return lidar_launch(l, nscan, 0, d_scan_world, d_sensor_pos, d_sensor_mat, d_ranges, d_geomid,
-                      d_dist, d_xyz, l->scene->stream);
+                      nullptr, d_dist, d_xyz, l->scene->stream);
 }
 
-int b2_lidar_cast(b2_lidar* l, int32_t nscan, const int32_t* scan_world, const double* sensor_pos,
-                  const double* sensor_mat, float* ranges, int32_t* geomid, double* dist,
-                  float* xyz) {
+int b2_lidar_cast_u16_device(b2_lidar* l, int32_t nscan, const int32_t* d_scan_world,
+                             const double* d_sensor_pos, const double* d_sensor_mat,
+                             float* d_ranges, uint16_t* d_geomid16) {
   if (!l) return fail(B2_ERR_INVALID, "null lidar");
   if (nscan < 0) return fail(B2_ERR_INVALID, "negative nscan");
-  if (nscan == 0 || l->nray == 0) return B2_OK;
+  if (nscan > 0 && (!d_sensor_pos || !d_sensor_mat)) return fail(B2_ERR_INVALID, "null sensor pose");
+  B2_CUDA(cudaSetDevice(l->scene->device));
+  return lidar_launch(l, nscan, 0, d_scan_world, d_sensor_pos, d_sensor_mat, d_ranges, nullptr,
+                      d_geomid16, nullptr, nullptr, l->scene->stream);
+}
+
+namespace {
+
+bool host_ptr_is_pinned(const void* p) {
+  if (!p) return true;
+  cudaPointerAttributes a{};
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return a.type == cudaMemoryTypeHost;
+}
+
+constexpr long long kSmallCastRays = 1 << 20;  // below this a host cast is one piece (and a graph)
+
+// the enqueue of one host cast, small path: H2D of the poses from pinned staging, the cast, D2H of
+// the results into pinned staging -- all on the scene's stream, all addresses fixed per lidar
+int enqueue_small(b2_lidar* l, const HostCast& hc, bool has_world, cudaStream_t stream) {
+  const size_t ns = (size_t)hc.nscan, n = hc.n;
+  B2_CUDA(cudaMemcpyAsync(l->d_spos.ptr, l->h_in.ptr, ns * 3 * sizeof(double),
+                          cudaMemcpyHostToDevice, stream));
+  B2_CUDA(cudaMemcpyAsync(l->d_smat.ptr, l->h_in.ptr + ns * 3, ns * 9 * sizeof(double),
+                          cudaMemcpyHostToDevice, stream));
+  if (has_world)
+    B2_CUDA(cudaMemcpyAsync(l->d_world.ptr, l->h_in.ptr + ns * 12, ns * sizeof(int32_t),
+                            cudaMemcpyHostToDevice, stream));
+  int rc = lidar_launch(l, hc.nscan, 0, has_world ? l->d_world.ptr : nullptr, l->d_spos.ptr,
+                        l->d_smat.ptr, hc.ranges ? l->d_ranges.ptr : nullptr,
+                        hc.geomid ? l->d_geomid.ptr : nullptr,
+                        hc.geomid16 ? l->d_geomid16.ptr : nullptr, hc.dist ? l->d_dist.ptr : nullptr,
+                        hc.xyz ? l->d_xyz.ptr : nullptr, stream);
+  if (rc != B2_OK) return rc;
+  unsigned char* o = l->h_out.ptr;
+  if (hc.ranges)
+    B2_CUDA(cudaMemcpyAsync(o + l->off_ranges, l->d_ranges.ptr, n * sizeof(float),
+                            cudaMemcpyDeviceToHost, stream));
+  if (hc.geomid)
+    B2_CUDA(cudaMemcpyAsync(o + l->off_geomid, l->d_geomid.ptr, n * sizeof(int32_t),
+                            cudaMemcpyDeviceToHost, stream));
+  if (hc.geomid16)
+    B2_CUDA(cudaMemcpyAsync(o + l->off_geomid16, l->d_geomid16.ptr, n * sizeof(uint16_t),
+                            cudaMemcpyDeviceToHost, stream));
+  if (hc.dist)
+    B2_CUDA(cudaMemcpyAsync(o + l->off_dist, l->d_dist.ptr, n * sizeof(double),
+                            cudaMemcpyDeviceToHost, stream));
+  if (hc.xyz)
+    B2_CUDA(cudaMemcpyAsync(o + l->off_xyz, l->d_xyz.ptr, n * 3 * sizeof(float),
+                            cudaMemcpyDeviceToHost, stream));
+  return B2_OK;
+}
+
+int lidar_cast_begin(b2_lidar* l, int32_t nscan, const int32_t* scan_world, const double* sensor_pos,
+                     const double* sensor_mat, float* ranges, int32_t* geomid, uint16_t* geomid16,
+                     double* dist, float* xyz) {
+  if (!l) return fail(B2_ERR_INVALID, "null lidar");
+  if (l->pend.active) return fail(B2_ERR_INVALID, "b2_lidar_cast_begin: the previous cast was not ended");
+  if (nscan < 0) return fail(B2_ERR_INVALID, "negative nscan");
+  HostCast hc;
+  hc.nscan = nscan;
+  hc.n = (size_t)nscan * l->nray;
+  hc.ranges = ranges;
+  hc.geomid = geomid;
+  hc.geomid16 = geomid16;
+  hc.dist = dist;
+  hc.xyz = xyz;
+  if (nscan == 0 || l->nray == 0) {
+    hc.active = true;
+    l->pend = hc;
+    return B2_OK;
+  }
   if (!sensor_pos || !sensor_mat) return fail(B2_ERR_INVALID, "null sensor pose");
   b2_scene* s = l->scene;
+  if (geomid16 && s->ngeom >= 65535)
+    return fail(B2_ERR_INVALID, "uint16 geom ids need a model with fewer than 65535 geoms");
+  if (s->ngeom > 0 && !s->topo_built)
+    return fail(B2_ERR_INVALID, "cast before the first b2_scene_update_poses");
   B2_CUDA(cudaSetDevice(s->device));
-  const size_t n = (size_t)nscan * l->nray;
-  B2_CUDA(l->d_spos.reserve((size_t)nscan * 3));
-  B2_CUDA(l->d_smat.reserve((size_t)nscan * 9));
-  if (scan_world) B2_CUDA(l->d_world.reserve((size_t)nscan));
+  // One scene-mutex hold for the whole enqueue: every piece of this cast sees the same pose
+  // snapshot (a concurrent refresh lands before or after all of them in stream order), and a
+  // caller that holds its own simulation mutex across this call gets sensor frames and geom poses
+  // of the same step.  Nothing below waits for the GPU.
+  std::lock_guard<std::recursive_mutex> lock(s->mtx);
+  {
+    int rc = flush_pending(s);
+    if (rc != B2_OK) return rc;
+  }
+  const size_t n = hc.n, ns = (size_t)nscan;
+  B2_CUDA(l->d_spos.reserve(ns * 3));
+  B2_CUDA(l->d_smat.reserve(ns * 9));
+  if (scan_world) B2_CUDA(l->d_world.reserve(ns));
   if (ranges) B2_CUDA(l->d_ranges.reserve(n));
   if (geomid) B2_CUDA(l->d_geomid.reserve(n));
+  if (geomid16) B2_CUDA(l->d_geomid16.reserve(n));
   if (dist) B2_CUDA(l->d_dist.reserve(n));
   if (xyz) B2_CUDA(l->d_xyz.reserve(n * 3));
-  B2_CUDA(cudaMemcpyAsync(l->d_spos.ptr, sensor_pos, (size_t)nscan * 3 * sizeof(double),
-                          cudaMemcpyHostToDevice, s->stream));
-  B2_CUDA(cudaMemcpyAsync(l->d_smat.ptr, sensor_mat, (size_t)nscan * 9 * sizeof(double),
-                          cudaMemcpyHostToDevice, s->stream));
+  hc.small = (long long)n <= env_int("B2_SMALL_CAST_RAYS", (int)kSmallCastRays);
+  hc.staged = hc.small || !(host_ptr_is_pinned(ranges) && host_ptr_is_pinned(geomid) &&
+                            host_ptr_is_pinned(geomid16) && host_ptr_is_pinned(dist) &&
+                            host_ptr_is_pinned(xyz));
+  if (hc.staged) {
+    auto up = [](size_t x) { return (x + 255) & ~(size_t)255; };
+    size_t off = 0;
+    l->off_ranges = off, off += ranges ? up(n * sizeof(float)) : 0;
+    l->off_geomid = off, off += geomid ? up(n * sizeof(int32_t)) : 0;
+    l->off_geomid16 = off, off += geomid16 ? up(n * sizeof(uint16_t)) : 0;
+    l->off_dist = off, off += dist ? up(n * sizeof(double)) : 0;
+    l->off_xyz = off, off += xyz ? up(n * 3 * sizeof(float)) : 0;
+    B2_CUDA(l->h_out.reserve(off + 256));
+  }
+  B2_CUDA(cudaEventRecord(l->cast_t0, s->stream));
+  if (hc.small) {
+    // ---- small path: one piece; the whole sequence is captured into a CUDA graph the second time
+    //      the same shape is asked for (a single scan is ~6 launches + copies: launch-gap bound)
+    B2_CUDA(l->h_in.reserve(ns * 13 + 16));
+    std::memcpy(l->h_in.ptr, sensor_pos, ns * 3 * sizeof(double));
+    std::memcpy(l->h_in.ptr + ns * 3, sensor_mat, ns * 9 * sizeof(double));
+    if (scan_world) std::memcpy(l->h_in.ptr + ns * 12, scan_world, ns * sizeof(int32_t));
+    const int mask = (ranges ? 1 : 0) | (geomid ? 2 : 0) | (geomid16 ? 4 : 0) | (dist ? 8 : 0) |
+                     (xyz ? 16 : 0);
+    LidarGraph& g = l->graph;
+    const bool same = g.nscan == nscan && g.mask == mask && g.topo_version == s->topo_version &&
+                      g.has_world == (scan_world != nullptr);
+    const bool use_graph = env_int("B2_GRAPH", 1) != 0;
+    if (use_graph && same && g.exec) {
+      B2_CUDA(cudaGraphLaunch(g.exec, s->stream));
+      g_launches += g.kernels;
+    } else if (use_graph && same && g.seen) {
+      cudaGraph_t graph = nullptr;
+      const long long l0 = g_launches.load();
+      B2_CUDA(cudaStreamBeginCapture(s->stream, cudaStreamCaptureModeThreadLocal));
+      int rc = enqueue_small(l, hc, scan_world != nullptr, s->stream);
+      cudaError_t e = cudaStreamEndCapture(s->stream, &graph);
+      g.kernels = (int)(g_launches.load() - l0);  // counted once here = the first replay
+      if (rc != B2_OK || e != cudaSuccess || !graph) {
+        if (graph) cudaGraphDestroy(graph);
+        cudaGetLastError();
+        g.seen = false;  // do not try again for this shape
+        g.nscan = -1;
+        rc = enqueue_small(l, hc, scan_world != nullptr, s->stream);
+        if (rc != B2_OK) return rc;
+      } else {
+        e = cudaGraphInstantiate(&g.exec, graph, 0);
+        cudaGraphDestroy(graph);
+        if (e != cudaSuccess) {
+          g.exec = nullptr;
+          cudaGetLastError();
+          rc = enqueue_small(l, hc, scan_world != nullptr, s->stream);
+          if (rc != B2_OK) return rc;
+        } else {
+          B2_CUDA(cudaGraphLaunch(g.exec, s->stream));
+        }
+      }
+    } else {
+      if (g.exec) {
+        cudaGraphExecDestroy(g.exec);
+        g.exec = nullptr;
+      }
+      g.nscan = nscan;
+      g.mask = mask;
+      g.topo_version = s->topo_version;
+      g.has_world = scan_world != nullptr;
+      g.seen = true;
+      int rc = enqueue_small(l, hc, scan_world != nullptr, s->stream);
+      if (rc != B2_OK) return rc;
+    }
+    B2_CUDA(cudaEventRecord(l->cast_t1, s->stream));
+    B2_CUDA(cudaEventRecord(l->all_done, s->stream));
+    hc.active = true;
+    l->pend = hc;
+    return B2_OK;
+  }
+
+  // ---- bulk path: cast piece k on the scene's stream while piece k-1 drains over PCIe on the copy
+  //      stream (the result read-back is up to 8 B/ray and would otherwise serialise behind the kernel)
+  B2_CUDA(cudaMemcpyAsync(l->d_spos.ptr, sensor_pos, ns * 3 * sizeof(double), cudaMemcpyHostToDevice,
+                          s->stream));
+  B2_CUDA(cudaMemcpyAsync(l->d_smat.ptr, sensor_mat, ns * 9 * sizeof(double), cudaMemcpyHostToDevice,
+                          s->stream));
   if (scan_world)
-    B2_CUDA(cudaMemcpyAsync(l->d_world.ptr, scan_world, (size_t)nscan * sizeof(int32_t),
-                            cudaMemcpyHostToDevice, s->stream));
-  // pipeline: cast chunk k on the compute stream while chunk k-1 drains over PCIe on the copy
-  // stream (the result read-back is 8 B/ray and would otherwise serialise behind the kernel)
-  // How many chunks: when the read-back is the longer leg it should start early and never wait
-  // (16 chunks: 6.3 of the 6.85 Grays/s the 54.8 GB/s link allows at 8 B/ray; 4 / 8 / 32 chunks gave
-  // 5.8 / 6.1 / 5.8); when the cast is the longer leg every extra chunk only adds launch tails
-  // (ranges only, 4 B/ray: 4 / 8 / 16 chunks gave 8.0 / 7.8 / 7.2).  The cast time per ray is known
-  // from the previous call on this lidar; the link is taken as 50 GB/s.
-  const double out_bytes = (ranges ? 4.0 : 0.0) + (geomid ? 4.0 : 0.0) + (dist ? 8.0 : 0.0) + (xyz ? 12.0 : 0.0);
+    B2_CUDA(cudaMemcpyAsync(l->d_world.ptr, scan_world, ns * sizeof(int32_t), cudaMemcpyHostToDevice,
+                            s->stream));
+  // How many pieces: when the read-back is the longer leg it should start early and never wait
+  // (16 pieces: 6.3 of the 6.85 Grays/s the 54.8 GB/s link allows at 8 B/ray; 4 / 8 / 32 gave
+  // 5.8 / 6.1 / 5.8); when the cast is the longer leg every extra piece only adds launch tails
+  // (ranges only, 4 B/ray: 4 / 8 / 16 gave 8.0 / 7.8 / 7.2).  The cast time per ray is known from
+  // the previous call on this lidar; the link is taken as 50 GB/s.
+  const double out_bytes = (ranges ? 4.0 : 0.0) + (geomid ? 4.0 : 0.0) + (geomid16 ? 2.0 : 0.0) +
+                           (dist ? 8.0 : 0.0) + (xyz ? 12.0 : 0.0);
   const double copy_ns_per_ray = out_bytes / 50.0;
   const double cast_ns_per_ray = l->cast_ns_per_ray > 0 ? l->cast_ns_per_ray : 0.12;
   int nchunk = env_int("B2_E2E_CHUNKS", copy_ns_per_ray > cast_ns_per_ray ? 16 : 4);
   if (nchunk > nscan) nchunk = nscan;
   if (nchunk < 1) nchunk = 1;
-  // equal chunks, except that the first and the last one are cut into quarters: nothing overlaps
-  // the cast of the first piece (the link idles until it is done -- what matters when the 8 B/ray
-  // read-back, not the cast, is the longer leg) nor the copy of the last piece
-  std::vector<int> bounds;
+  // equal pieces, except that the first and the last one are cut into quarters: nothing overlaps
+  // the cast of the first piece nor the copy of the last one
+  std::vector<int>& bounds = hc.bounds;
   for (int c = 0; c < nchunk; c++) {
     const int b0 = (int)((long long)nscan * c / nchunk), b1 = (int)((long long)nscan * (c + 1) / nchunk);
     if (bounds.empty() || b0 > bounds.back()) bounds.push_back(b0);
@@ -897,41 +1268,128 @@ int b2_lidar_cast(b2_lidar* l, int32_t nscan, const int32_t* scan_world, const d
     }
   }
   bounds.push_back(nscan);
-  B2_CUDA(cudaEventRecord(l->cast_t0, s->stream));
+  while (l->piece_done.size() + 1 < bounds.size()) {
+    cudaEvent_t ev = nullptr;
+    B2_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    l->piece_done.push_back(ev);
+  }
+  unsigned char* o = l->h_out.ptr;
   for (size_t c = 0; c + 1 < bounds.size(); c++) {
     const int s0 = bounds[c], s1 = bounds[c + 1];
-    const int ns = s1 - s0;
-    if (ns <= 0) continue;
-    const size_t off = (size_t)s0 * l->nray, cnt = (size_t)ns * l->nray;
-    int rc = lidar_launch(l, ns, s0, scan_world ? l->d_world.ptr + s0 : nullptr, l->d_spos.ptr + 3 * (size_t)s0,
-                          l->d_smat.ptr + 9 * (size_t)s0, ranges ? l->d_ranges.ptr + off : nullptr,
-                          geomid ? l->d_geomid.ptr + off : nullptr, dist ? l->d_dist.ptr + off : nullptr,
-                          xyz ? l->d_xyz.ptr + 3 * off : nullptr, s->stream);
+    const int npc = s1 - s0;
+    const size_t off = (size_t)s0 * l->nray, cnt = (size_t)npc * l->nray;
+    int rc = lidar_launch(l, npc, s0, scan_world ? l->d_world.ptr + s0 : nullptr,
+                          l->d_spos.ptr + 3 * (size_t)s0, l->d_smat.ptr + 9 * (size_t)s0,
+                          ranges ? l->d_ranges.ptr + off : nullptr,
+                          geomid ? l->d_geomid.ptr + off : nullptr,
+                          geomid16 ? l->d_geomid16.ptr + off : nullptr,
+                          dist ? l->d_dist.ptr + off : nullptr, xyz ? l->d_xyz.ptr + 3 * off : nullptr,
+                          s->stream);
     if (rc != B2_OK) return rc;
-    cudaEvent_t ev = l->chunk_done[c & 1];
+    cudaEvent_t ev = l->piece_done[c];
     B2_CUDA(cudaEventRecord(ev, s->stream));
     B2_CUDA(cudaStreamWaitEvent(s->copy_stream, ev, 0));
+    const bool st = hc.staged;
     if (ranges)
-      B2_CUDA(cudaMemcpyAsync(ranges + off, l->d_ranges.ptr + off, cnt * sizeof(float),
-                              cudaMemcpyDeviceToHost, s->copy_stream));
+      B2_CUDA(cudaMemcpyAsync(st ? (void*)(o + l->off_ranges + off * 4) : (void*)(ranges + off),
+                              l->d_ranges.ptr + off, cnt * sizeof(float), cudaMemcpyDeviceToHost,
+                              s->copy_stream));
     if (geomid)
-      B2_CUDA(cudaMemcpyAsync(geomid + off, l->d_geomid.ptr + off, cnt * sizeof(int32_t),
-                              cudaMemcpyDeviceToHost, s->copy_stream));
+      B2_CUDA(cudaMemcpyAsync(st ? (void*)(o + l->off_geomid + off * 4) : (void*)(geomid + off),
+                              l->d_geomid.ptr + off, cnt * sizeof(int32_t), cudaMemcpyDeviceToHost,
+                              s->copy_stream));
+    if (geomid16)
+      B2_CUDA(cudaMemcpyAsync(st ? (void*)(o + l->off_geomid16 + off * 2) : (void*)(geomid16 + off),
+                              l->d_geomid16.ptr + off, cnt * sizeof(uint16_t), cudaMemcpyDeviceToHost,
+                              s->copy_stream));
     if (dist)
-      B2_CUDA(cudaMemcpyAsync(dist + off, l->d_dist.ptr + off, cnt * sizeof(double),
-                              cudaMemcpyDeviceToHost, s->copy_stream));
+      B2_CUDA(cudaMemcpyAsync(st ? (void*)(o + l->off_dist + off * 8) : (void*)(dist + off),
+                              l->d_dist.ptr + off, cnt * sizeof(double), cudaMemcpyDeviceToHost,
+                              s->copy_stream));
     if (xyz)
-      B2_CUDA(cudaMemcpyAsync(xyz + 3 * off, l->d_xyz.ptr + 3 * off, cnt * 3 * sizeof(float),
-                              cudaMemcpyDeviceToHost, s->copy_stream));
+      B2_CUDA(cudaMemcpyAsync(st ? (void*)(o + l->off_xyz + off * 12) : (void*)(xyz + 3 * off),
+                              l->d_xyz.ptr + 3 * off, cnt * 3 * sizeof(float), cudaMemcpyDeviceToHost,
+                              s->copy_stream));
+    // the same event, re-recorded on the copy stream: piece c has landed on the host
+    B2_CUDA(cudaEventRecord(ev, s->copy_stream));
   }
   B2_CUDA(cudaEventRecord(l->cast_t1, s->stream));
-  B2_CUDA(cudaStreamSynchronize(s->stream));
-  B2_CUDA(cudaStreamSynchronize(s->copy_stream));
-  float cast_ms = 0.f;
-  if (cudaEventElapsedTime(&cast_ms, l->cast_t0, l->cast_t1) == cudaSuccess && cast_ms > 0.f)
-    l->cast_ns_per_ray = (double)cast_ms * 1e6 / (double)n;
+  hc.active = true;
+  l->pend = hc;
   return B2_OK;
 }
+
+int lidar_cast_end(b2_lidar* l) {
+  if (!l) return fail(B2_ERR_INVALID, "null lidar");
+  if (!l->pend.active) return fail(B2_ERR_INVALID, "b2_lidar_cast_end without b2_lidar_cast_begin");
+  HostCast hc = l->pend;
+  l->pend = HostCast{};
+  if (hc.nscan == 0 || l->nray == 0) return B2_OK;
+  b2_scene* s = l->scene;
+  B2_CUDA(cudaSetDevice(s->device));
+  const unsigned char* o = l->h_out.ptr;
+  const size_t n = hc.n;
+  if (hc.small) {
+    B2_CUDA(cudaEventSynchronize(l->all_done));
+    if (hc.ranges) std::memcpy(hc.ranges, o + l->off_ranges, n * sizeof(float));
+    if (hc.geomid) std::memcpy(hc.geomid, o + l->off_geomid, n * sizeof(int32_t));
+    if (hc.geomid16) std::memcpy(hc.geomid16, o + l->off_geomid16, n * sizeof(uint16_t));
+    if (hc.dist) std::memcpy(hc.dist, o + l->off_dist, n * sizeof(double));
+    if (hc.xyz) std::memcpy(hc.xyz, o + l->off_xyz, n * 3 * sizeof(float));
+  } else {
+    for (size_t c = 0; c + 1 < hc.bounds.size(); c++) {
+      B2_CUDA(cudaEventSynchronize(l->piece_done[c]));
+      if (!hc.staged) continue;
+      // pageable destination: drain the landed piece while the later ones are still in flight
+      const size_t off = (size_t)hc.bounds[c] * l->nray;
+      const size_t cnt = (size_t)(hc.bounds[c + 1] - hc.bounds[c]) * l->nray;
+      if (hc.ranges) std::memcpy(hc.ranges + off, o + l->off_ranges + off * 4, cnt * 4);
+      if (hc.geomid) std::memcpy(hc.geomid + off, o + l->off_geomid + off * 4, cnt * 4);
+      if (hc.geomid16) std::memcpy(hc.geomid16 + off, o + l->off_geomid16 + off * 2, cnt * 2);
+      if (hc.dist) std::memcpy(hc.dist + off, o + l->off_dist + off * 8, cnt * 8);
+      if (hc.xyz) std::memcpy(hc.xyz + 3 * off, o + l->off_xyz + off * 12, cnt * 12);
+    }
+  }
+  float cast_ms = 0.f;
+  if (cudaEventElapsedTime(&cast_ms, l->cast_t0, l->cast_t1) == cudaSuccess && cast_ms > 0.f) {
+    l->cast_ns_per_ray = (double)cast_ms * 1e6 / (double)n;
+    l->last_device_us = (double)cast_ms * 1e3;
+  } else {
+    cudaGetLastError();
+  }
+  return B2_OK;
+}
+
+}  // namespace
+
+int b2_lidar_cast_begin(b2_lidar* l, int32_t nscan, const int32_t* scan_world,
+                        const double* sensor_pos, const double* sensor_mat, float* ranges,
+                        int32_t* geomid, double* dist, float* xyz) {
+  return lidar_cast_begin(l, nscan, scan_world, sensor_pos, sensor_mat, ranges, geomid, nullptr, dist,
+                          xyz);
+}
+
+int b2_lidar_cast_end(b2_lidar* l) { return lidar_cast_end(l); }
+
+int b2_lidar_cast(b2_lidar* l, int32_t nscan, const int32_t* scan_world, const double* sensor_pos,
+                  const double* sensor_mat, float* ranges, int32_t* geomid, double* dist,
+                  float* xyz) {
+  int rc = lidar_cast_begin(l, nscan, scan_world, sensor_pos, sensor_mat, ranges, geomid, nullptr,
+                            dist, xyz);
+  if (rc != B2_OK) return rc;
+  return lidar_cast_end(l);
+}
+
+int b2_lidar_cast_u16(b2_lidar* l, int32_t nscan, const int32_t* scan_world,
+                      const double* sensor_pos, const double* sensor_mat, float* ranges,
+                      uint16_t* geomid16) {
+  int rc = lidar_cast_begin(l, nscan, scan_world, sensor_pos, sensor_mat, ranges, nullptr, geomid16,
+                            nullptr, nullptr);
+  if (rc != B2_OK) return rc;
+  return lidar_cast_end(l);
+}
+
+double b2_lidar_last_device_us(const b2_lidar* l) { return l ? l->last_device_us : 0.0; }
 
 // ---------------------------------------------------------------------------------------------
 // mj_multiRay-shaped entry
@@ -1049,6 +1507,9 @@ int b2_camera_destroy(b2_camera* c) {
   c->d_pos.release();
   c->d_mat.release();
   c->d_world.release();
+  c->h_in.release();
+  c->h_out.release();
+  if (c->done) cudaEventDestroy(c->done);
   if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
   delete c;
   return B2_OK;
@@ -1076,6 +1537,9 @@ int b2_depth_to_cloud_device(b2_camera* c, int32_t ncam, const float* d_gl_depth
   if (ncam == 0) return B2_OK;
   if (!d_gl_depth) return fail(B2_ERR_INVALID, "null depth buffer");
   B2_CUDA(cudaSetDevice(c->device));
+  // a camera bound to a scene enqueues on the scene's stream: serialise with the scene's other users
+  std::unique_lock<std::recursive_mutex> lock;
+  if (c->scene) lock = std::unique_lock<std::recursive_mutex>(c->scene->mtx);
   DepthParams p{};
   p.gl_depth = d_gl_depth;
   p.depth_out = d_depth32fc1;
@@ -1136,9 +1600,12 @@ int b2_camera_render_depth_device(b2_camera* c, int32_t ncam, const int32_t* d_c
     return fail(B2_ERR_INVALID, "render before the first b2_scene_update_poses");
   B2_CUDA(cudaSetDevice(s->device));
   if (c->d_elim.cap == 0) {
-    // the renderer hides only invisible geoms (alpha 0); no body / group / static exclusion
+    // what mjv_updateScene draws with the reference's mjv_defaultOption
+    // (ref:src/mujoco_cameras.cpp:165): geom groups 0-2 on, 3-5 off (collision geoms live in group 3
+    // in the converter's output), alpha-0 geoms invisible; no body / static exclusion
+    static const uint8_t kDefaultGroups[B2_NGROUP] = {1, 1, 1, 0, 0, 0};
     std::vector<uint8_t> elim;
-    eliminate_flags(s->hm, nullptr, 1, -1, elim);
+    eliminate_flags(s->hm, c->desc.geomgroup_set ? c->desc.geomgroup : kDefaultGroups, 1, -1, elim);
     B2_CUDA(c->d_elim.reserve(elim.size() + 1));
     if (!elim.empty())
       B2_CUDA(cudaMemcpy(c->d_elim.ptr, elim.data(), elim.size(), cudaMemcpyHostToDevice));
@@ -1176,32 +1643,56 @@ int b2_rgb_flip_device(b2_camera* c, int32_t ncam, const uint8_t* d_rgb_gl, uint
   return B2_OK;
 }
 
-int b2_camera_render_to_cloud(b2_camera* c, int32_t ncam, const int32_t* cam_world,
-                              const double* cam_pos, const double* cam_mat, float* gl_depth,
-                              float* depth32fc1, void* cloud) {
+int b2_camera_render_to_cloud_begin(b2_camera* c, int32_t ncam, const int32_t* cam_world,
+                                    const double* cam_pos, const double* cam_mat, float* gl_depth,
+                                    float* depth32fc1, void* cloud) {
   if (!c) return fail(B2_ERR_INVALID, "null camera");
   if (!c->scene) return fail(B2_ERR_INVALID, "camera was created without a scene");
+  if (c->pend.active) return fail(B2_ERR_INVALID, "render_to_cloud_begin: the previous render was not ended");
   if (ncam < 0) return fail(B2_ERR_INVALID, "negative ncam");
-  if (ncam == 0) return B2_OK;
+  c->pend.ncam = ncam;
+  c->pend.gl_depth = gl_depth;
+  c->pend.depth32fc1 = depth32fc1;
+  c->pend.cloud = cloud;
+  if (ncam == 0) {
+    c->pend.active = true;
+    return B2_OK;
+  }
   if (!cam_pos || !cam_mat) return fail(B2_ERR_INVALID, "null camera pose");
+  b2_scene* s = c->scene;
   B2_CUDA(cudaSetDevice(c->device));
+  if (!c->done) B2_CUDA(cudaEventCreateWithFlags(&c->done, cudaEventDisableTiming));
   const size_t npix = (size_t)ncam * c->desc.width * c->desc.height;
   const size_t pf = (size_t)c->desc.point_step / 4;
-  B2_CUDA(c->d_pos.reserve((size_t)ncam * 3));
-  B2_CUDA(c->d_mat.reserve((size_t)ncam * 9));
+  const size_t nc = (size_t)ncam;
+  // one scene-mutex hold for the whole enqueue (poses, render, linearise + cloud, read-back): see
+  // lidar_cast_begin.  Results are staged through pinned memory; _end copies them out.
+  std::lock_guard<std::recursive_mutex> lock(s->mtx);
+  B2_CUDA(c->d_pos.reserve(nc * 3));
+  B2_CUDA(c->d_mat.reserve(nc * 9));
   B2_CUDA(c->d_in.reserve(npix));
   if (depth32fc1) B2_CUDA(c->d_depth.reserve(npix));
   if (cloud) B2_CUDA(c->d_cloud.reserve(npix * pf));
+  B2_CUDA(c->h_in.reserve(nc * 13 + 16));
+  auto up = [](size_t x) { return (x + 255) & ~(size_t)255; };
+  size_t off = 0;
+  c->pend.off_gl = off, off += gl_depth ? up(npix * 4) : 0;
+  c->pend.off_depth = off, off += depth32fc1 ? up(npix * 4) : 0;
+  c->pend.off_cloud = off, off += cloud ? up(npix * pf * 4) : 0;
+  B2_CUDA(c->h_out.reserve(off + 256));
+  std::memcpy(c->h_in.ptr, cam_pos, nc * 3 * sizeof(double));
+  std::memcpy(c->h_in.ptr + nc * 3, cam_mat, nc * 9 * sizeof(double));
   int32_t* d_world = nullptr;
   if (cam_world) {
-    B2_CUDA(c->d_world.reserve((size_t)ncam));
-    B2_CUDA(cudaMemcpyAsync(c->d_world.ptr, cam_world, (size_t)ncam * sizeof(int32_t),
+    B2_CUDA(c->d_world.reserve(nc));
+    std::memcpy(c->h_in.ptr + nc * 12, cam_world, nc * sizeof(int32_t));
+    B2_CUDA(cudaMemcpyAsync(c->d_world.ptr, c->h_in.ptr + nc * 12, nc * sizeof(int32_t),
                             cudaMemcpyHostToDevice, c->stream));
     d_world = c->d_world.ptr;
   }
-  B2_CUDA(cudaMemcpyAsync(c->d_pos.ptr, cam_pos, (size_t)ncam * 3 * sizeof(double),
-                          cudaMemcpyHostToDevice, c->stream));
-  B2_CUDA(cudaMemcpyAsync(c->d_mat.ptr, cam_mat, (size_t)ncam * 9 * sizeof(double),
+  B2_CUDA(cudaMemcpyAsync(c->d_pos.ptr, c->h_in.ptr, nc * 3 * sizeof(double), cudaMemcpyHostToDevice,
+                          c->stream));
+  B2_CUDA(cudaMemcpyAsync(c->d_mat.ptr, c->h_in.ptr + nc * 3, nc * 9 * sizeof(double),
                           cudaMemcpyHostToDevice, c->stream));
   int rc = b2_camera_render_depth_device(c, ncam, d_world, c->d_pos.ptr, c->d_mat.ptr, c->d_in.ptr);
   if (rc != B2_OK) return rc;
@@ -1210,17 +1701,44 @@ int b2_camera_render_to_cloud(b2_camera* c, int32_t ncam, const int32_t* cam_wor
                                   cloud ? c->d_cloud.ptr : nullptr);
     if (rc != B2_OK) return rc;
   }
+  unsigned char* o = c->h_out.ptr;
   if (gl_depth)
-    B2_CUDA(cudaMemcpyAsync(gl_depth, c->d_in.ptr, npix * sizeof(float), cudaMemcpyDeviceToHost,
-                            c->stream));
+    B2_CUDA(cudaMemcpyAsync(o + c->pend.off_gl, c->d_in.ptr, npix * sizeof(float),
+                            cudaMemcpyDeviceToHost, c->stream));
   if (depth32fc1)
-    B2_CUDA(cudaMemcpyAsync(depth32fc1, c->d_depth.ptr, npix * sizeof(float),
+    B2_CUDA(cudaMemcpyAsync(o + c->pend.off_depth, c->d_depth.ptr, npix * sizeof(float),
                             cudaMemcpyDeviceToHost, c->stream));
   if (cloud)
-    B2_CUDA(cudaMemcpyAsync(cloud, c->d_cloud.ptr, npix * pf * sizeof(float),
+    B2_CUDA(cudaMemcpyAsync(o + c->pend.off_cloud, c->d_cloud.ptr, npix * pf * sizeof(float),
                             cudaMemcpyDeviceToHost, c->stream));
-  B2_CUDA(cudaStreamSynchronize(c->stream));
+  B2_CUDA(cudaEventRecord(c->done, c->stream));
+  c->pend.active = true;
   return B2_OK;
+}
+
+int b2_camera_render_to_cloud_end(b2_camera* c) {
+  if (!c) return fail(B2_ERR_INVALID, "null camera");
+  if (!c->pend.active) return fail(B2_ERR_INVALID, "render_to_cloud_end without render_to_cloud_begin");
+  c->pend.active = false;
+  if (c->pend.ncam == 0) return B2_OK;
+  B2_CUDA(cudaSetDevice(c->device));
+  B2_CUDA(cudaEventSynchronize(c->done));
+  const size_t npix = (size_t)c->pend.ncam * c->desc.width * c->desc.height;
+  const size_t pf = (size_t)c->desc.point_step / 4;
+  const unsigned char* o = c->h_out.ptr;
+  if (c->pend.gl_depth) std::memcpy(c->pend.gl_depth, o + c->pend.off_gl, npix * 4);
+  if (c->pend.depth32fc1) std::memcpy(c->pend.depth32fc1, o + c->pend.off_depth, npix * 4);
+  if (c->pend.cloud) std::memcpy(c->pend.cloud, o + c->pend.off_cloud, npix * pf * 4);
+  return B2_OK;
+}
+
+int b2_camera_render_to_cloud(b2_camera* c, int32_t ncam, const int32_t* cam_world,
+                              const double* cam_pos, const double* cam_mat, float* gl_depth,
+                              float* depth32fc1, void* cloud) {
+  int rc = b2_camera_render_to_cloud_begin(c, ncam, cam_world, cam_pos, cam_mat, gl_depth, depth32fc1,
+                                           cloud);
+  if (rc != B2_OK) return rc;
+  return b2_camera_render_to_cloud_end(c);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -176,6 +176,53 @@ class Lidar:
                                            _ptr(out.get("dist")), _ptr(out.get("xyz"))))
         return out
 
+    def cast_begin(self, sensor_pos, sensor_mat, scan_world=None, want=("ranges", "geomid"), out=None):
+        """b2_lidar_cast_begin: enqueue only.  Returns the dict ``cast_end`` will have filled."""
+        pos = np.ascontiguousarray(sensor_pos, np.float64).reshape(-1, 3)
+        mat = np.ascontiguousarray(sensor_mat, np.float64).reshape(-1, 9)
+        s = pos.shape[0]
+        sw = None if scan_world is None else np.ascontiguousarray(scan_world, np.int32)
+        out = dict(out or {})
+        shapes = {"ranges": ((s, self.nray), np.float32), "geomid": ((s, self.nray), np.int32),
+                  "dist": ((s, self.nray), np.float64), "xyz": ((s, self.nray, 3), np.float32)}
+        for k in want:
+            if k not in out:
+                out[k] = np.empty(shapes[k][0], shapes[k][1])
+        self._pending = (pos, mat, sw, out)  # the arrays must outlive the call
+        _capi.check(self.lib.b2_lidar_cast_begin(self._h, s, _ptr(sw), _ptr(pos), _ptr(mat),
+                                                 _ptr(out.get("ranges")), _ptr(out.get("geomid")),
+                                                 _ptr(out.get("dist")), _ptr(out.get("xyz"))))
+        return out
+
+    def cast_end(self):
+        _capi.check(self.lib.b2_lidar_cast_end(self._h))
+        out = self._pending[3]
+        self._pending = None
+        return out
+
+    def cast_u16(self, sensor_pos, sensor_mat, scan_world=None, out=None):
+        """ranges f32 + geom ids as uint16 (0xFFFF = miss): 6 B/ray over the host link."""
+        pos = np.ascontiguousarray(sensor_pos, np.float64).reshape(-1, 3)
+        mat = np.ascontiguousarray(sensor_mat, np.float64).reshape(-1, 9)
+        s = pos.shape[0]
+        sw = None if scan_world is None else np.ascontiguousarray(scan_world, np.int32)
+        out = dict(out or {})
+        if "ranges" not in out:
+            out["ranges"] = np.empty((s, self.nray), np.float32)
+        if "geomid16" not in out:
+            out["geomid16"] = np.empty((s, self.nray), np.uint16)
+        _capi.check(self.lib.b2_lidar_cast_u16(self._h, s, _ptr(sw), _ptr(pos), _ptr(mat),
+                                               _ptr(out["ranges"]), _ptr(out["geomid16"])))
+        return out
+
+    def cast_u16_device(self, nscan, d_pos, d_mat, d_world=None, ranges=None, geomid16=None):
+        _capi.check(self.lib.b2_lidar_cast_u16_device(self._h, int(nscan), _ptr(d_world), _ptr(d_pos),
+                                                      _ptr(d_mat), _ptr(ranges), _ptr(geomid16)))
+
+    def last_device_us(self) -> float:
+        """device time of the last host cast (first enqueue .. last kernel), microseconds"""
+        return float(self.lib.b2_lidar_last_device_us(self._h))
+
     def cast_device(self, nscan, d_pos, d_mat, d_world=None, ranges=None, geomid=None, dist=None,
                     xyz=None):
         """Device path (async): all arguments are torch CUDA tensors (or None)."""
@@ -193,6 +240,11 @@ class DepthCamera:
         self.scene = scene
         d = _capi.CameraDesc(spec.width, spec.height, spec.fovy, spec.znear, spec.zfar, spec.extent,
                              spec.point_step)
+        gg = getattr(spec, "geomgroup", None)  # None: mjv_defaultOption (groups 0-2 visible)
+        if gg is not None:
+            for i in range(6):
+                d.geomgroup[i] = int(gg[i])
+            d.geomgroup_set = 1
         h = C.c_void_p()
         _capi.check(self.lib.b2_camera_create(scene._h if scene else None, device, C.byref(d),
                                               C.byref(h)))
@@ -239,6 +291,19 @@ class DepthCamera:
     def rgb_flip_device(self, ncam, d_rgb_gl, d_rgb_out):
         """uint8 CUDA tensors [ncam,H,W,3]: GL bottom-up rows -> Image top-down rows."""
         _capi.check(self.lib.b2_rgb_flip_device(self._h, int(ncam), _ptr(d_rgb_gl), _ptr(d_rgb_out)))
+
+    def render_to_cloud(self, cam_pos, cam_mat, cam_world=None, want=("gl", "depth", "cloud")):
+        """Host path: ray-cast GL depth of the camera poses, then linearise + flip + cloud."""
+        pos = np.ascontiguousarray(cam_pos, np.float64).reshape(-1, 3)
+        mat = np.ascontiguousarray(cam_mat, np.float64).reshape(-1, 9)
+        n, h, w = pos.shape[0], self.spec.height, self.spec.width
+        sw = None if cam_world is None else np.ascontiguousarray(cam_world, np.int32)
+        gl = np.empty((n, h, w), np.float32) if "gl" in want else None
+        depth = np.empty((n, h, w), np.float32) if "depth" in want else None
+        cloud = np.empty((n, h, w, self.spec.point_step // 4), np.float32) if "cloud" in want else None
+        _capi.check(self.lib.b2_camera_render_to_cloud(self._h, n, _ptr(sw), _ptr(pos), _ptr(mat),
+                                                       _ptr(gl), _ptr(depth), _ptr(cloud)))
+        return gl, depth, cloud
 
     def render_depth_device(self, ncam, d_pos, d_mat, d_gl_depth, d_world=None):
         _capi.check(self.lib.b2_camera_render_depth_device(self._h, int(ncam), _ptr(d_world),

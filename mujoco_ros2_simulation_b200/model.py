@@ -135,6 +135,7 @@ class CameraSpec:
     zfar: float = 50.0
     extent: float = 1.0
     point_step: int = 12
+    geomgroup: tuple | None = None  # geom groups the ray-cast renderer draws; None = mjv_defaultOption
 
 
 # ------------------------------------------------------------------------------------------------

@@ -28,6 +28,8 @@
 #include <array>
 #include <chrono>
 #include <cstdint>
+#include <cstdio>
+#include <cstdlib>
 #include <memory>
 #include <string>
 #include <thread>
@@ -198,9 +200,24 @@ private:
   size_t count_ = 0;
 };
 
+// logging stand-in: messages are kept (tests read them) and echoed to stderr when B2_COMPAT_LOG is set
+struct Logger {
+  std::shared_ptr<std::vector<std::string>> lines = std::make_shared<std::vector<std::string>>();
+  void log(const char* level, const std::string& text) const {
+    lines->push_back(std::string(level) + ": " + text);
+    if (std::getenv("B2_COMPAT_LOG")) std::fprintf(stderr, "[%s] %s\n", level, text.c_str());
+  }
+};
+
 class Node {
 public:
   using SharedPtr = std::shared_ptr<Node>;
+  const Logger& get_logger() const { return logger_; }
+
+private:
+  Logger logger_;
+
+public:
   template <class MsgT>
   typename Publisher<MsgT>::SharedPtr create_publisher(const std::string& topic, size_t /*depth*/) {
     return std::make_shared<Publisher<MsgT>>(topic);
@@ -224,6 +241,17 @@ private:
   double period_;
 };
 }  // namespace rclcpp
+
+// printf-style, like the real macros; the stream variants take `a << b`
+#define B2_COMPAT_LOGF(level, logger, ...)              \
+  do {                                                  \
+    char b2_buf_[512];                                  \
+    std::snprintf(b2_buf_, sizeof(b2_buf_), __VA_ARGS__); \
+    (logger).log(level, b2_buf_);                       \
+  } while (0)
+#define RCLCPP_INFO(logger, ...) B2_COMPAT_LOGF("INFO", logger, __VA_ARGS__)
+#define RCLCPP_WARN(logger, ...) B2_COMPAT_LOGF("WARN", logger, __VA_ARGS__)
+#define RCLCPP_ERROR(logger, ...) B2_COMPAT_LOGF("ERROR", logger, __VA_ARGS__)
 
 #endif  // B2_HAVE_ROS2
 #endif

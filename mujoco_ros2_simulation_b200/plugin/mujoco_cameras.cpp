@@ -1,26 +1,33 @@
 // mujoco_cameras.cpp -- B200 drop-in for ref:src/mujoco_cameras.cpp (see mujoco_cameras.hpp).
+//
+// Interface-compatible re-implementation.  Class and method names, the URDF sensor parameter names,
+// topic defaults and the Image / CameraInfo field values follow the reference file
+// (yassine-cherni/mujoco_ros2_simulation, src/mujoco_cameras.cpp, Copyright (c) 2025 United States
+// Government as represented by the Administrator of NASA, Apache License 2.0,
+// http://www.apache.org/licenses/LICENSE-2.0) because a drop-in has to; each such spot cites its
+// ref: line.  The PointCloud2 message, the GPU objects and update() are new.  The reference text
+// itself is not reproduced: integration/ carries the change as a patch against the reference tree.
 #include "mujoco_cameras.hpp"
 
+#include <algorithm>
 #include <cmath>
 #include <cstring>
-#include <optional>
 
 namespace mujoco_ros2_control
 {
 
 namespace
 {
-std::optional<hardware_interface::ComponentInfo>
-get_sensor_from_info(const hardware_interface::HardwareInfo& hardware_info, const std::string& name)
+// one sensor_msgs/Image header for a W x H image of `channel_bytes` bytes per pixel
+void describe_image(sensor_msgs::msg::Image& img, const std::string& frame, uint32_t w, uint32_t h,
+                    uint32_t bytes_per_pixel, const char* encoding)
 {
-  for (const auto& sensor : hardware_info.sensors)
-  {
-    if (sensor.name == name)
-    {
-      return sensor;
-    }
-  }
-  return std::nullopt;
+  img.header.frame_id = frame;
+  img.width = w;
+  img.height = h;
+  img.step = w * bytes_per_pixel;
+  img.encoding = encoding;
+  img.data.assign(static_cast<size_t>(w) * h * bytes_per_pixel, 0);
 }
 }  // namespace
 
@@ -40,98 +47,94 @@ MujocoCameras::~MujocoCameras()
   close();
 }
 
-// ref:src/mujoco_cameras.cpp:40-129 -- same defaults, same message fields
+// One CameraData per mjModel camera (ref:src/mujoco_cameras.cpp:40-129): resolution and fovy from the
+// model, topics and frame from the URDF <sensor> of the same name or the reference's defaults
+// (<name>_frame, <name>/camera_info, <name>/color, <name>/depth, ref :71-74), pinhole intrinsics
+// ref :119-124.  New: the organised PointCloud2 on <depth_topic>/points.
 void MujocoCameras::register_cameras(const hardware_interface::HardwareInfo& hardware_info)
 {
-  cameras_.resize(0);
-  for (auto i = 0; i < mj_model_->ncam; ++i)
+  cameras_.clear();
+  for (int id = 0; id < mj_model_->ncam; ++id)
   {
-    const char* cam_name = mj_model_->names + mj_model_->name_camadr[i];
-    const int* cam_resolution = mj_model_->cam_resolution + 2 * i;
-    const mjtNum cam_fovy = mj_model_->cam_fovy[i];
+    CameraData cam;
+    cam.cam_id = id;
+    cam.name = mj_model_->names + mj_model_->name_camadr[id];
+    cam.width = static_cast<uint32_t>(mj_model_->cam_resolution[2 * id]);
+    cam.height = static_cast<uint32_t>(mj_model_->cam_resolution[2 * id + 1]);
 
-    CameraData camera;
-    camera.cam_id = i;
-    camera.name = cam_name;
-    camera.width = static_cast<uint32_t>(cam_resolution[0]);
-    camera.height = static_cast<uint32_t>(cam_resolution[1]);
-
-    const auto camera_info_maybe = get_sensor_from_info(hardware_info, cam_name);
-    if (camera_info_maybe.has_value())
+    const auto sensor = std::find_if(hardware_info.sensors.begin(), hardware_info.sensors.end(),
+                                     [&](const hardware_interface::ComponentInfo& c) { return c.name == cam.name; });
+    if (sensor != hardware_info.sensors.end())
     {
-      // all-or-nothing: .at() throws if one is missing, as in the reference (:63-66)
-      const auto camera_info = camera_info_maybe.value();
-      camera.frame_name = camera_info.parameters.at("frame_name");
-      camera.info_topic = camera_info.parameters.at("info_topic");
-      camera.image_topic = camera_info.parameters.at("image_topic");
-      camera.depth_topic = camera_info.parameters.at("depth_topic");
+      // all four or an exception, as in the reference (.at(), ref :63-66)
+      const auto& prm = sensor->parameters;
+      cam.frame_name = prm.at("frame_name");
+      cam.info_topic = prm.at("info_topic");
+      cam.image_topic = prm.at("image_topic");
+      cam.depth_topic = prm.at("depth_topic");
     }
     else
     {
-      camera.frame_name = camera.name + "_frame";
-      camera.info_topic = camera.name + "/camera_info";
-      camera.image_topic = camera.name + "/color";
-      camera.depth_topic = camera.name + "/depth";
+      cam.frame_name = cam.name + "_frame";
+      cam.info_topic = cam.name + "/camera_info";
+      cam.image_topic = cam.name + "/color";
+      cam.depth_topic = cam.name + "/depth";
     }
-    camera.points_topic = camera.depth_topic + "/points";
+    cam.points_topic = cam.depth_topic + "/points";
 
-    camera.camera_info_pub = node_->create_publisher<sensor_msgs::msg::CameraInfo>(camera.info_topic, 1);
-    camera.image_pub = node_->create_publisher<sensor_msgs::msg::Image>(camera.image_topic, 1);
-    camera.depth_image_pub = node_->create_publisher<sensor_msgs::msg::Image>(camera.depth_topic, 1);
-    camera.cloud_pub = node_->create_publisher<sensor_msgs::msg::PointCloud2>(camera.points_topic, 1);
+    cam.camera_info_pub = node_->create_publisher<sensor_msgs::msg::CameraInfo>(cam.info_topic, 1);
+    cam.image_pub = node_->create_publisher<sensor_msgs::msg::Image>(cam.image_topic, 1);
+    cam.depth_image_pub = node_->create_publisher<sensor_msgs::msg::Image>(cam.depth_topic, 1);
+    cam.cloud_pub = node_->create_publisher<sensor_msgs::msg::PointCloud2>(cam.points_topic, 1);
 
-    camera.image.header.frame_id = camera.frame_name;
-    const auto image_size = camera.width * camera.height * 3;
-    camera.image_buffer.resize(image_size);
-    camera.image.data.resize(image_size);
-    camera.image.width = camera.width;
-    camera.image.height = camera.height;
-    camera.image.step = camera.width * 3;
-    camera.image.encoding = sensor_msgs::image_encodings::RGB8;
+    const size_t npix = static_cast<size_t>(cam.width) * cam.height;
+    describe_image(cam.image, cam.frame_name, cam.width, cam.height, 3, sensor_msgs::image_encodings::RGB8);
+    describe_image(cam.depth_image, cam.frame_name, cam.width, cam.height, sizeof(float),
+                   sensor_msgs::image_encodings::TYPE_32FC1);
+    cam.image_buffer.assign(npix * 3, 0);
+    cam.depth_buffer.assign(npix, 0.0f);
 
-    camera.depth_image.header.frame_id = camera.frame_name;
-    camera.depth_buffer.resize(camera.width * camera.height);
-    camera.depth_image.data.resize(camera.width * camera.height * sizeof(float));
-    camera.depth_image.width = camera.width;
-    camera.depth_image.height = camera.height;
-    camera.depth_image.step = camera.width * sizeof(float);
-    camera.depth_image.encoding = sensor_msgs::image_encodings::TYPE_32FC1;
-
-    camera.camera_info.header.frame_id = camera.frame_name;
-    camera.camera_info.width = camera.width;
-    camera.camera_info.height = camera.height;
-    camera.camera_info.distortion_model = "plumb_bob";
-    camera.camera_info.k.fill(0.0);
-    camera.camera_info.r.fill(0.0);  // left all-zero by the reference (:115); kept
-    camera.camera_info.p.fill(0.0);
-    camera.camera_info.d.resize(5, 0.0);
-    double focal_scaling = (1.0 / std::tan((cam_fovy * M_PI / 180.0) / 2.0)) * camera.height / 2.0;
-    camera.camera_info.k[0] = camera.camera_info.p[0] = focal_scaling;
-    camera.camera_info.k[2] = camera.camera_info.p[2] = static_cast<double>(camera.width) / 2.0;
-    camera.camera_info.k[4] = camera.camera_info.p[5] = focal_scaling;
-    camera.camera_info.k[5] = camera.camera_info.p[6] = static_cast<double>(camera.height) / 2.0;
-    camera.camera_info.k[8] = camera.camera_info.p[10] = 1.0;
+    // CameraInfo: plumb_bob with five zero coefficients, K and P from fovy (ref :119-124); R stays
+    // all-zero exactly as the reference leaves it (ref :115)
+    auto& info = cam.camera_info;
+    info.header.frame_id = cam.frame_name;
+    info.width = cam.width;
+    info.height = cam.height;
+    info.distortion_model = "plumb_bob";
+    info.d.assign(5, 0.0);
+    info.k.fill(0.0);
+    info.r.fill(0.0);
+    info.p.fill(0.0);
+    const double f = (1.0 / std::tan((mj_model_->cam_fovy[id] * M_PI / 180.0) / 2.0)) * cam.height / 2.0;
+    const double cx = static_cast<double>(cam.width) / 2.0, cy = static_cast<double>(cam.height) / 2.0;
+    info.k[0] = info.k[4] = info.p[0] = info.p[5] = f;
+    info.k[2] = info.p[2] = cx;
+    info.k[5] = info.p[6] = cy;
+    info.k[8] = info.p[10] = 1.0;
 
     // PointCloud2: organised, x/y/z FLOAT32 at 0/4/8, point_step 12, NaN for invalid depth
-    camera.cloud.header.frame_id = camera.frame_name;
-    camera.cloud.height = camera.height;
-    camera.cloud.width = camera.width;
-    camera.cloud.fields.resize(3);
-    const char* names[3] = { "x", "y", "z" };
-    for (int f = 0; f < 3; ++f)
+    auto& cloud = cam.cloud;
+    cloud.header.frame_id = cam.frame_name;
+    cloud.height = cam.height;
+    cloud.width = cam.width;
+    cloud.fields.resize(3);
+    for (int k = 0; k < 3; ++k)
     {
-      camera.cloud.fields[f].name = names[f];
-      camera.cloud.fields[f].offset = 4 * f;
-      camera.cloud.fields[f].datatype = sensor_msgs::msg::PointField::FLOAT32;
-      camera.cloud.fields[f].count = 1;
+      cloud.fields[k].name = std::string(1, "xyz"[k]);
+      cloud.fields[k].offset = 4 * k;
+      cloud.fields[k].datatype = sensor_msgs::msg::PointField::FLOAT32;
+      cloud.fields[k].count = 1;
     }
-    camera.cloud.is_bigendian = false;
-    camera.cloud.point_step = 12;
-    camera.cloud.row_step = camera.width * 12;
-    camera.cloud.is_dense = false;
-    camera.cloud.data.resize((size_t)camera.width * camera.height * 12);
+    cloud.is_bigendian = false;
+    cloud.is_dense = false;
+    cloud.point_step = 12;
+    cloud.row_step = cam.width * cloud.point_step;
+    cloud.data.assign(npix * cloud.point_step, 0);
 
-    cameras_.push_back(camera);
+    RCLCPP_INFO(node_->get_logger(), "camera '%s': %ux%u fovy %.2f, frame %s, topics %s %s %s %s", cam.name.c_str(),
+                cam.width, cam.height, static_cast<double>(mj_model_->cam_fovy[id]), cam.frame_name.c_str(),
+                cam.image_topic.c_str(), cam.depth_topic.c_str(), cam.info_topic.c_str(), cam.points_topic.c_str());
+    cameras_.push_back(std::move(cam));
   }
 }
 
@@ -153,7 +156,7 @@ bool MujocoCameras::create_engines()
     d.point_step = 12;
     if (b2_camera_create(mirror_ ? mirror_->handle() : nullptr, 0, &d, &camera.engine) != B2_OK)
     {
-      last_error_ = std::string("b2_camera_create: ") + b2_last_error();
+      report_failure(std::string("b2_camera_create: ") + b2_last_error());
       return false;
     }
   }
@@ -199,70 +202,119 @@ void MujocoCameras::update_loop()
   }
 }
 
+// One publish cycle (ref:src/mujoco_cameras.cpp:199-265).  With a GL readback hook the reference's
+// steps 0-2 stay (render + mjr_readPixels) and step 3 -- float32 linearise + flip, ref :222-240 -- runs
+// on the GPU together with the cloud projection.  Without OpenGL the depth buffer is ray-cast from
+// the scene mirror: the camera frames are read and the render is ENQUEUED while the sim mutex is
+// held (b2_camera_render_to_cloud_begin, nothing waits for the GPU), so frames and geom poses belong
+// to the same physics step -- what mjv_copyData under the same mutex gives the reference (:205-208).
 void MujocoCameras::update()
 {
-  // Step 1: under the sim mutex take the camera poses (and refresh the mirror in shim v0)
-  std::vector<double> pos(3 * cameras_.size()), mat(9 * cameras_.size());
+  const size_t nc = cameras_.size();
+  std::vector<char> fresh(nc, 0), rgb_fresh(nc, 0);
+  if (!gl_readback_)
   {
-    std::unique_lock<std::recursive_mutex> lock(*sim_mutex_);
-    if (refresh_in_update_ && mirror_ != nullptr)
+    pose_scratch_.resize(12 * nc);
+    std::vector<char> begun(nc, 0);
     {
-      mirror_->refresh(mj_data_);
+      std::unique_lock<std::recursive_mutex> lock(*sim_mutex_);
+      if (refresh_in_update_ && mirror_ != nullptr)
+      {
+        mirror_->refresh(mj_data_);
+      }
+      for (size_t k = 0; k < nc; ++k)
+      {
+        auto& cam = cameras_[k];
+        double* pos = &pose_scratch_[12 * k];
+        std::copy_n(mj_data_->cam_xpos + 3 * cam.cam_id, 3, pos);
+        std::copy_n(mj_data_->cam_xmat + 9 * cam.cam_id, 9, pos + 3);
+        if (b2_camera_render_to_cloud_begin(cam.engine, 1, nullptr, pos, pos + 3, cam.depth_buffer.data(),
+                                            reinterpret_cast<float*>(cam.depth_image.data.data()),
+                                            cam.cloud.data.data()) == B2_OK)
+        {
+          begun[k] = 1;
+        }
+        else
+        {
+          report_failure(std::string("render_to_cloud_begin (") + cam.name + "): " + b2_last_error());
+        }
+      }
     }
-    for (size_t k = 0; k < cameras_.size(); ++k)
+    for (size_t k = 0; k < nc; ++k)
     {
-      std::memcpy(&pos[3 * k], mj_data_->cam_xpos + 3 * cameras_[k].cam_id, 3 * sizeof(double));
-      std::memcpy(&mat[9 * k], mj_data_->cam_xmat + 9 * cameras_[k].cam_id, 9 * sizeof(double));
-    }
-  }
-
-  for (size_t k = 0; k < cameras_.size(); ++k)
-  {
-    auto& camera = cameras_[k];
-    float* depth_out = reinterpret_cast<float*>(camera.depth_image.data.data());
-    int rc;
-    if (gl_readback_)
-    {
-      // Step 2 (reference path): GL render + readback fills depth_buffer / image_buffer;
-      // Step 3 on the GPU: linearise + flip + cloud in one kernel
-      if (!gl_readback_(camera))
+      if (!begun[k])
       {
         continue;
       }
-      rc = b2_depth_to_cloud(camera.engine, 1, camera.depth_buffer.data(), depth_out, camera.cloud.data.data());
-      // RGB: GL origin is bottom-left, flip row by row (:243-249)
-      const auto row_size = camera.width * 3;
-      for (uint32_t h = 0; h < camera.height; h++)
+      if (b2_camera_render_to_cloud_end(cameras_[k].engine) == B2_OK)
       {
-        std::memcpy(&camera.image.data[(camera.height - 1 - h) * row_size], &camera.image_buffer[h * row_size],
-                    row_size);
+        fresh[k] = 1;
+      }
+      else
+      {
+        report_failure(std::string("render_to_cloud_end (") + cameras_[k].name + "): " + b2_last_error());
       }
     }
-    else
+  }
+  else
+  {
+    for (size_t k = 0; k < nc; ++k)
     {
-      // no OpenGL: depth by ray casting the scene mirror, then the same fused step 3
-      rc = b2_camera_render_to_cloud(camera.engine, 1, nullptr, &pos[3 * k], &mat[9 * k], camera.depth_buffer.data(),
-                                     depth_out, camera.cloud.data.data());
-    }
-    if (rc != B2_OK)
-    {
-      last_error_ = std::string("camera update: ") + b2_last_error();
-      return;
+      auto& cam = cameras_[k];
+      if (!gl_readback_(cam))
+      {
+        report_failure("GL readback failed for camera " + cam.name);
+        continue;
+      }
+      if (b2_depth_to_cloud(cam.engine, 1, cam.depth_buffer.data(), reinterpret_cast<float*>(cam.depth_image.data.data()),
+                            cam.cloud.data.data()) != B2_OK)
+      {
+        report_failure(std::string("b2_depth_to_cloud (") + cam.name + "): " + b2_last_error());
+        continue;
+      }
+      // RGB: GL's origin is bottom-left; the message wants the top row first (ref :243-249)
+      const size_t row = static_cast<size_t>(cam.width) * 3;
+      for (uint32_t h = 0; h < cam.height; ++h)
+      {
+        std::copy_n(&cam.image_buffer[h * row], row, &cam.image.data[(cam.height - 1 - h) * row]);
+      }
+      fresh[k] = rgb_fresh[k] = 1;
     }
   }
 
-  // Step 4: publish
-  for (auto& camera : cameras_)
+  // publish what this cycle produced: nothing stale goes out with a fresh stamp, and no colour image
+  // exists unless a GL readback filled it (ray casting renders depth only)
+  for (size_t k = 0; k < nc; ++k)
   {
-    const auto time = node_->now();
-    camera.image.header.stamp = time;
-    camera.depth_image.header.stamp = time;
-    camera.camera_info.header.stamp = time;
-    camera.cloud.header.stamp = time;
-    camera.image_pub->publish(camera.image);
-    camera.depth_image_pub->publish(camera.depth_image);
-    camera.camera_info_pub->publish(camera.camera_info);
-    camera.cloud_pub->publish(camera.cloud);
+    if (!fresh[k])
+    {
+      continue;
+    }
+    auto& cam = cameras_[k];
+    const auto stamp = node_->now();
+    cam.depth_image.header.stamp = stamp;
+    cam.camera_info.header.stamp = stamp;
+    cam.cloud.header.stamp = stamp;
+    if (rgb_fresh[k])
+    {
+      cam.image.header.stamp = stamp;
+      cam.image_pub->publish(cam.image);
+    }
+    cam.depth_image_pub->publish(cam.depth_image);
+    cam.camera_info_pub->publish(cam.camera_info);
+    cam.cloud_pub->publish(cam.cloud);
+  }
+}
+
+void MujocoCameras::report_failure(const std::string& what)
+{
+  {
+    std::lock_guard<std::mutex> g(error_mutex_);
+    last_error_ = what;
+  }
+  if (failures_++ % 50 == 0)
+  {
+    RCLCPP_ERROR(node_->get_logger(), "%s", what.c_str());
   }
 }
 

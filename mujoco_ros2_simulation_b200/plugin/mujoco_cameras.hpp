@@ -1,5 +1,10 @@
 // mujoco_cameras.hpp -- B200 drop-in for ref:include/mujoco_ros2_control/mujoco_cameras.hpp.
 //
+// Interface-compatible re-implementation: class / method / field names mirror the reference header
+// (yassine-cherni/mujoco_ros2_simulation, Copyright (c) 2025 United States Government as represented
+// by the Administrator of NASA, Apache License 2.0) because the plugin that constructs this class
+// must not notice the swap; the PointCloud2 members, the GPU members and update() are new.
+//
 // Same class and public methods (register_cameras / init / close), same URDF sensor parameters
 // (frame_name, info_topic, image_topic, depth_topic -- all-or-nothing, ref:src/mujoco_cameras.cpp:63-66),
 // same Image / CameraInfo fields (:91-124, including the all-zero CameraInfo.r quirk).  Step 3 of
@@ -82,8 +87,9 @@ public:
   {
     return cameras_;
   }
-  const std::string& last_error() const
+  std::string last_error() const
   {
+    std::lock_guard<std::mutex> g(error_mutex_);
     return last_error_;
   }
   void set_refresh_in_update(bool v)
@@ -93,6 +99,7 @@ public:
 
 private:
   void update_loop();
+  void report_failure(const std::string& what);
 
   rclcpp::Node::SharedPtr node_;
   std::recursive_mutex* sim_mutex_{ nullptr };
@@ -106,7 +113,10 @@ private:
   std::vector<CameraData> cameras_;
   std::thread rendering_thread_;
   std::atomic_bool publish_images_{ false };
+  std::vector<double> pose_scratch_;  // [12 per camera] camera frames of the cycle in flight
+  mutable std::mutex error_mutex_;
   std::string last_error_;
+  unsigned failures_{ 0 };
 };
 
 }  // namespace mujoco_ros2_control

@@ -1,5 +1,10 @@
 // mujoco_lidar.hpp -- B200 drop-in for ref:include/mujoco_ros2_control/mujoco_lidar.hpp.
 //
+// Interface-compatible re-implementation: class / method / field names mirror the reference header
+// (yassine-cherni/mujoco_ros2_simulation, Copyright (c) 2025 United States Government as represented
+// by the Administrator of NASA, Apache License 2.0) because the plugin that constructs this class
+// must not notice the swap; the GPU members and update() are new.
+//
 // Same class, same public methods (register_lidar / init / close), same URDF sensor parameters
 // (frame_name, min_angle, max_angle, angle_increment, laserscan_topic, range_min, range_max) and
 // the same LaserScan message (ref:src/mujoco_lidar.cpp:54-112).  What changes is where the ranges
@@ -45,7 +50,8 @@ struct LidarData
   std::vector<uint8_t> have_ray;    // a rangefinder sensor was found for index i
   int bodyid{ -1 };                 // site_bodyid: the rangefinder's bodyexclude
   double site_pos[3]{ 0, 0, 0 };    // common site position in that body
-  double cutoff{ 0.0 };             // sensor_cutoff
+  double cutoff{ 0.0 };             // sensor_cutoff (one per lidar: register_lidar checks)
+  std::vector<double> ray_cutoff;   // sensor_cutoff of each replica
   b2_lidar* engine{ nullptr };
 
   // For message publishing
@@ -85,8 +91,9 @@ public:
   {
     return lidar_sensors_;
   }
-  const std::string& last_error() const
+  std::string last_error() const
   {
+    std::lock_guard<std::mutex> g(error_mutex_);
     return last_error_;
   }
   // When the physics thread does not call SceneMirror::refresh after mj_step (shim v0), update()
@@ -98,6 +105,7 @@ public:
 
 private:
   void update_loop();
+  void report_failure(const std::string& what);
 
   rclcpp::Node::SharedPtr node_;
   std::recursive_mutex* sim_mutex_{ nullptr };
@@ -108,9 +116,12 @@ private:
   bool refresh_in_update_{ true };
 
   std::vector<LidarData> lidar_sensors_;
+  std::vector<double> pose_scratch_;  // [12 per lidar] sensor frames of the cycle in flight
   std::thread rendering_thread_;
   std::atomic_bool publish_lidar_{ false };
+  mutable std::mutex error_mutex_;
   std::string last_error_;
+  unsigned failures_{ 0 };
 };
 
 }  // namespace mujoco_ros2_control

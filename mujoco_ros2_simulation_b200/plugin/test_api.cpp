@@ -2,11 +2,17 @@
 // MujocoSystemInterface does: construct + register in on_init, init/update in on_activate, close in
 // the destructor (ref:src/mujoco_system_interface.cpp:707-717, 938-939, 467-476).  Only compiled
 // with the stand-in ROS 2 / MuJoCo types of b2_compat.hpp.
+#include <algorithm>
+#include <atomic>
+#include <chrono>
+#include <cmath>
 #include <cstring>
 #include <memory>
 #include <mutex>
 #include <sstream>
 #include <string>
+#include <thread>
+#include <vector>
 
 #include "mujoco_cameras.hpp"
 #include "mujoco_lidar.hpp"
@@ -276,6 +282,103 @@ int b2p_camera_rgb(void* hp, int k, uint8_t* rgb_published, uint8_t* rgb_gl)
   std::memcpy(rgb_published, c.image_pub->last().data.data(), c.image.data.size());
   std::memcpy(rgb_gl, c.image_buffer.data(), c.image_buffer.size());
   return (int)c.image.data.size();
+}
+
+// A9 / SURVEY B3: what the physics thread pays for SceneMirror::refresh while a sensor thread keeps
+// the GPU busy.  Thread A casts an (n_el x n_az)-ray lidar back to back through the blocking ABI;
+// thread B plays PhysicsLoop at `hz`: lock the sim mutex, move the geoms a little ("mj_step"),
+// refresh the mirror, unlock.  out = {p50, p99, max refresh time in microseconds, casts completed,
+// refreshes done}.  Returns 0, or a negative code with b2p_error set.
+int b2p_refresh_stress(void* hp, int n_el, int n_az, double hz, double seconds, double* out)
+{
+  auto* h = static_cast<Harness*>(hp);
+  if (!h->mirror)
+  {
+    h->error = "b2p_refresh_stress before b2p_activate";
+    return -1;
+  }
+  // a 3-D fan around the first lidar's body frame
+  std::vector<double> dirs((size_t)n_el * n_az * 3);
+  for (int e = 0; e < n_el; ++e)
+  {
+    const double el = -0.4 + 0.6 * e / std::max(1, n_el - 1);
+    for (int a = 0; a < n_az; ++a)
+    {
+      const double az = 6.283185307179586 * a / n_az;
+      double* d = &dirs[((size_t)e * n_az + a) * 3];
+      d[0] = std::cos(el) * std::cos(az);
+      d[1] = std::cos(el) * std::sin(az);
+      d[2] = std::sin(el);
+    }
+  }
+  b2_lidar_desc desc{};
+  desc.nray = n_el * n_az;
+  desc.local_dir = dirs.data();
+  desc.tile_w = n_az;
+  desc.flg_static = 1;
+  desc.bodyexclude = -1;
+  desc.range_max = 1000.0;
+  b2_lidar* big = nullptr;
+  {
+    std::unique_lock<std::recursive_mutex> lock(h->mtx);
+    h->mirror->refresh(h->d);  // first poses (topology) if nobody did it yet
+  }
+  if (b2_lidar_create(h->mirror->handle(), &desc, &big) != B2_OK)
+  {
+    h->error = b2_last_error();
+    return -2;
+  }
+  std::atomic_bool stop{ false };
+  std::atomic_int casts{ 0 }, cast_fail{ 0 };
+  std::thread sensor([&]() {
+    std::vector<float> ranges((size_t)desc.nray);
+    const double pos[3] = { 0.5, 0.5, 0.8 };
+    const double mat[9] = { 1, 0, 0, 0, 1, 0, 0, 0, 1 };
+    while (!stop)
+    {
+      if (b2_lidar_cast(big, 1, nullptr, pos, mat, ranges.data(), nullptr, nullptr, nullptr) != B2_OK)
+      {
+        cast_fail++;
+        break;
+      }
+      casts++;
+    }
+  });
+  std::vector<double> us;
+  const auto t_start = std::chrono::steady_clock::now();
+  const auto period = std::chrono::duration<double>(1.0 / hz);
+  int tick = 0;
+  while (std::chrono::duration<double>(std::chrono::steady_clock::now() - t_start).count() < seconds)
+  {
+    {
+      std::unique_lock<std::recursive_mutex> lock(h->mtx);
+      for (int g = 0; g < h->m->ngeom; ++g)
+      {
+        h->d->geom_xpos[3 * g] += (tick & 1) ? 1e-4 : -1e-4;  // the stand-in for mj_step
+      }
+      const auto a = std::chrono::steady_clock::now();
+      h->mirror->refresh(h->d);
+      const auto b = std::chrono::steady_clock::now();
+      us.push_back(std::chrono::duration<double, std::micro>(b - a).count());
+    }
+    ++tick;
+    std::this_thread::sleep_until(t_start + tick * period);
+  }
+  stop = true;
+  sensor.join();
+  b2_lidar_destroy(big);
+  if (cast_fail)
+  {
+    h->error = std::string("cast failed: ") + b2_last_error();
+    return -3;
+  }
+  std::sort(us.begin(), us.end());
+  out[0] = us.empty() ? 0 : us[us.size() / 2];
+  out[1] = us.empty() ? 0 : us[(size_t)((us.size() - 1) * 0.99)];
+  out[2] = us.empty() ? 0 : us.back();
+  out[3] = casts;
+  out[4] = (double)us.size();
+  return 0;
 }
 
 void b2p_destroy(void* hp)

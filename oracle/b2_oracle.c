@@ -529,9 +529,20 @@ double orc_ray(const orc_model* m, const orc_data* d, const double pnt[3], const
 }
 
 /* ------------------------------------------------------------------------------------------
- * A.6 mj_multiRay: one origin, per-geom eliminate flags computed once, per-geom bounding-sphere
- * cull (upstream culls per body with an azimuth/elevation rectangle; both are pure accelerators
- * and leave the A.5 result unchanged), geoms visited in index order, same update rule.
+ * A.6 mj_multiRay: one origin for all rays; per-geom eliminate flags computed once; a cull that
+ * skips geoms a ray cannot reach; the surviving geoms are visited in index order with the A.5 update
+ * rule, so the result equals orc_ray per ray (hits beyond `cutoff` are reported as misses).
+ *   ORC_CULL_BODY_ANGULAR (A.6 as specified): per body the (azimuth, elevation) rectangle of its
+ *     bounding box as seen from pnt; a ray whose own (azimuth, elevation) falls outside skips the
+ *     whole body.  A body that contains the origin, carries an unbounded plane, or whose azimuth
+ *     range exceeds pi (it wraps) keeps the full range; a body whose box is farther than cutoff is
+ *     dropped.  The body box is the union of its geoms' world boxes (mjModel's body BVH root is
+ *     not part of the scene mirror).  Elevation bounds are taken from the box's z range and its
+ *     nearest / farthest horizontal distance, not from its 8 corners only: the corner extremes are
+ *     not conservative for a box edge passing close to the vertical through pnt.
+ *   ORC_CULL_GEOM_SPHERE: per geom, distance of its bounding sphere from the ray's line -- what the
+ *     body cull degenerates to with one geom per body; the stronger accelerator on scenes whose
+ *     bodies are spatially scattered.
  * ---------------------------------------------------------------------------------------- */
 typedef struct {
   const orc_model* m;
@@ -539,8 +550,15 @@ typedef struct {
   const double* pnt;
   const double* vec;
   const uint8_t* elim;
-  const double* bs_c; /* per-geom bounding sphere centre - pnt */
+  int cull;
+  /* ORC_CULL_GEOM_SPHERE */
+  const double* bs_c;  /* per-geom bounding sphere centre - pnt */
   const double* bs_r2; /* radius^2, <0: no cull (plane) */
+  /* ORC_CULL_BODY_ANGULAR */
+  const double* body_ba;   /* [nbody*4] az_min, el_min, az_max, el_max */
+  const uint8_t* body_on;  /* [nbody] body has a live geom within cutoff */
+  const int32_t* body_adr; /* [nbody+1] into body_geom */
+  const int32_t* body_geom; /* geoms of each body, ascending */
   int32_t* geomid;
   double* dist;
   int begin, end;
@@ -555,21 +573,41 @@ static void multi_ray_range(const multi_job* J) {
     int32_t id = -1;
     const double vv = dot3(v, v);
     if (vv >= ORC_MINVAL) {
-      for (int g = 0; g < m->ngeom; g++) {
-        if (J->elim[g]) continue;
-        if (J->bs_r2[g] >= 0) {
-          /* squared distance from sphere centre to the ray's line, and side test */
-          const double* c = J->bs_c + 3 * g;
-          const double cc = dot3(c, c), cv = dot3(c, v);
-          if (cc > J->bs_r2[g]) {
-            if (cv <= 0) continue;
-            if (cc * vv - cv * cv > J->bs_r2[g] * vv * (1 + 1e-9)) continue;
+      if (J->cull == ORC_CULL_BODY_ANGULAR) {
+        const double az = atan2(v[1], v[0]);
+        const double el = atan2(v[2], sqrt(v[0] * v[0] + v[1] * v[1]));
+        for (int b = 0; b < m->nbody; b++) {
+          if (!J->body_on[b]) continue;
+          const double* ba = J->body_ba + 4 * b;
+          if (az < ba[0] || el < ba[1] || az > ba[2] || el > ba[3]) continue;
+          for (int k = J->body_adr[b]; k < J->body_adr[b + 1]; k++) {
+            const int g = J->body_geom[k];
+            const double nd = ray_one_geom(m, J->d, g, J->pnt, v);
+            /* bodies are visited in id order; geom ids need not be body-major, so the tie rule
+             * is made explicit (identical to strict '<' for MuJoCo's body-major geom order) */
+            if (nd >= 0 && (dist < 0 || nd < dist || (nd == dist && g < id))) {
+              dist = nd;
+              id = g;
+            }
           }
         }
-        const double nd = ray_one_geom(m, J->d, g, J->pnt, v);
-        if (nd >= 0 && (nd < dist || dist < 0)) {
-          dist = nd;
-          id = g;
+      } else {
+        for (int g = 0; g < m->ngeom; g++) {
+          if (J->elim[g]) continue;
+          if (J->cull == ORC_CULL_GEOM_SPHERE && J->bs_r2[g] >= 0) {
+            /* squared distance from sphere centre to the ray's line, and side test */
+            const double* c = J->bs_c + 3 * g;
+            const double cc = dot3(c, c), cv = dot3(c, v);
+            if (cc > J->bs_r2[g]) {
+              if (cv <= 0) continue;
+              if (cc * vv - cv * cv > J->bs_r2[g] * vv * (1 + 1e-9)) continue;
+            }
+          }
+          const double nd = ray_one_geom(m, J->d, g, J->pnt, v);
+          if (nd >= 0 && (nd < dist || dist < 0)) {
+            dist = nd;
+            id = g;
+          }
         }
       }
     }
@@ -587,36 +625,70 @@ static void* multi_ray_thread(void* arg) {
   return NULL;
 }
 
-void orc_multi_ray(const orc_model* m, const orc_data* d, const double pnt[3], const double* vec,
-                   const uint8_t* geomgroup, uint8_t flg_static, int bodyexclude, int32_t* geomid,
-                   double* dist, int nray, double cutoff, int nthread) {
-  uint8_t* elim = (uint8_t*)malloc((size_t)m->ngeom + 1);
-  double* bs_c = (double*)malloc(sizeof(double) * 3 * ((size_t)m->ngeom + 1));
-  double* bs_r2 = (double*)malloc(sizeof(double) * ((size_t)m->ngeom + 1));
+/* radius of a sphere around geom_xpos that contains the geom; < 0: unbounded (plane) */
+static double geom_bound_radius(const orc_model* m, int g) {
+  const double* s = m->geom_size + 3 * g;
+  switch (m->geom_type[g]) {
+    case ORC_GEOM_SPHERE:
+      return s[0];
+    case ORC_GEOM_CAPSULE:
+      return s[0] + s[1];
+    case ORC_GEOM_CYLINDER:
+      return sqrt(s[0] * s[0] + s[1] * s[1]);
+    case ORC_GEOM_ELLIPSOID:
+      return fmax(s[0], fmax(s[1], s[2]));
+    case ORC_GEOM_BOX:
+    case ORC_GEOM_MESH:
+      return sqrt(s[0] * s[0] + s[1] * s[1] + s[2] * s[2]);
+    default:
+      return -1;
+  }
+}
+
+/* world box of geom g (lo[3], hi[3]); returns 0 for an unbounded geom */
+static int geom_world_box(const orc_model* m, const orc_data* d, int g, double lo[3], double hi[3]) {
+  const double* s = m->geom_size + 3 * g;
+  const double* p = d->geom_xpos + 3 * g;
+  const double* R = d->geom_xmat + 9 * g;
+  const int t = m->geom_type[g];
+  if (t == ORC_GEOM_PLANE) return 0;
+  for (int k = 0; k < 3; k++) {
+    const double r0 = R[3 * k], r1 = R[3 * k + 1], r2 = R[3 * k + 2];
+    double e;
+    if (t == ORC_GEOM_SPHERE) {
+      e = s[0];
+    } else if (t == ORC_GEOM_CAPSULE) {
+      e = fabs(r2) * s[1] + s[0];
+    } else if (t == ORC_GEOM_CYLINDER) {
+      const double q = 1.0 - r2 * r2;
+      e = fabs(r2) * s[1] + s[0] * sqrt(q > 0 ? q : 0.0);
+    } else if (t == ORC_GEOM_ELLIPSOID) {
+      e = sqrt(r0 * r0 * s[0] * s[0] + r1 * r1 * s[1] * s[1] + r2 * r2 * s[2] * s[2]);
+    } else {
+      e = fabs(r0) * s[0] + fabs(r1) * s[1] + fabs(r2) * s[2];
+    }
+    e = e * (1 + 1e-9) + 1e-12;
+    lo[k] = p[k] - e;
+    hi[k] = p[k] + e;
+  }
+  return 1;
+}
+
+void orc_multi_ray_cull(const orc_model* m, const orc_data* d, const double pnt[3],
+                        const double* vec, const uint8_t* geomgroup, uint8_t flg_static,
+                        int bodyexclude, int32_t* geomid, double* dist, int nray, double cutoff,
+                        int nthread, int cull) {
+  const size_t G = (size_t)m->ngeom, B = (size_t)m->nbody;
+  uint8_t* elim = (uint8_t*)malloc(G + 1);
+  double* bs_c = (double*)malloc(sizeof(double) * 3 * (G + 1));
+  double* bs_r2 = (double*)malloc(sizeof(double) * (G + 1));
+  double* body_ba = (double*)malloc(sizeof(double) * 4 * (B + 1));
+  uint8_t* body_on = (uint8_t*)calloc(B + 1, 1);
+  int32_t* body_adr = (int32_t*)calloc(B + 2, sizeof(int32_t));
+  int32_t* body_geom = (int32_t*)malloc(sizeof(int32_t) * (G + 1));
   for (int g = 0; g < m->ngeom; g++) {
     elim[g] = (uint8_t)orc_ray_eliminate(m, g, geomgroup, flg_static, bodyexclude);
-    const double* s = m->geom_size + 3 * g;
-    double r;
-    switch (m->geom_type[g]) {
-      case ORC_GEOM_SPHERE:
-        r = s[0];
-        break;
-      case ORC_GEOM_CAPSULE:
-        r = s[0] + s[1];
-        break;
-      case ORC_GEOM_CYLINDER:
-        r = sqrt(s[0] * s[0] + s[1] * s[1]);
-        break;
-      case ORC_GEOM_ELLIPSOID:
-        r = fmax(s[0], fmax(s[1], s[2]));
-        break;
-      case ORC_GEOM_BOX:
-      case ORC_GEOM_MESH:
-        r = sqrt(s[0] * s[0] + s[1] * s[1] + s[2] * s[2]);
-        break;
-      default:
-        r = -1;
-    }
+    double r = geom_bound_radius(m, g);
     if (r >= 0) {
       r *= 1 + 1e-9;
       bs_r2[g] = r * r;
@@ -625,12 +697,78 @@ void orc_multi_ray(const orc_model* m, const orc_data* d, const double pnt[3], c
     }
     for (int j = 0; j < 3; j++) bs_c[3 * g + j] = d->geom_xpos[3 * g + j] - pnt[j];
   }
+  if (cull == ORC_CULL_BODY_ANGULAR) {
+    /* geoms of each body (not eliminated), ascending geom id */
+    for (int g = 0; g < m->ngeom; g++)
+      if (!elim[g]) body_adr[m->geom_bodyid[g] + 1]++;
+    for (size_t b = 0; b < B; b++) body_adr[b + 1] += body_adr[b];
+    int32_t* fill = (int32_t*)malloc(sizeof(int32_t) * (B + 1));
+    for (size_t b = 0; b < B; b++) fill[b] = body_adr[b];
+    for (int g = 0; g < m->ngeom; g++)
+      if (!elim[g]) body_geom[fill[m->geom_bodyid[g]]++] = g;
+    free(fill);
+    for (int b = 0; b < m->nbody; b++) {
+      double* ba = body_ba + 4 * b;
+      ba[0] = -M_PI, ba[1] = -M_PI, ba[2] = M_PI, ba[3] = M_PI; /* full range */
+      if (body_adr[b + 1] == body_adr[b]) continue;                /* no live geom */
+      double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
+      int bounded = 1;
+      for (int k = body_adr[b]; k < body_adr[b + 1]; k++) {
+        double gl[3], gh[3];
+        if (!geom_world_box(m, d, body_geom[k], gl, gh)) {
+          bounded = 0;
+          break;
+        }
+        for (int j = 0; j < 3; j++) {
+          lo[j] = fmin(lo[j], gl[j]);
+          hi[j] = fmax(hi[j], gh[j]);
+        }
+      }
+      body_on[b] = 1;
+      if (!bounded) continue;
+      /* box relative to the origin of the rays */
+      double near2 = 0;
+      int inside = 1;
+      for (int j = 0; j < 3; j++) {
+        lo[j] -= pnt[j];
+        hi[j] -= pnt[j];
+        const double gap = fmax(fmax(lo[j], -hi[j]), 0.0);
+        near2 += gap * gap;
+        if (gap > 0) inside = 0;
+      }
+      if (near2 > cutoff * cutoff) { /* farther than cutoff: nothing of it can be reported */
+        body_on[b] = 0;
+        continue;
+      }
+      if (inside) continue;
+      /* azimuth range from the 4 vertical edges; wrap-around or the vertical through pnt crossing
+       * the box's footprint disable the cull */
+      if (lo[0] <= 0 && hi[0] >= 0 && lo[1] <= 0 && hi[1] >= 0) continue;
+      double az0 = 1e300, az1 = -1e300, rho_max = 0;
+      for (int c = 0; c < 4; c++) {
+        const double x = (c & 1) ? hi[0] : lo[0], y = (c & 2) ? hi[1] : lo[1];
+        const double az = atan2(y, x);
+        az0 = fmin(az0, az);
+        az1 = fmax(az1, az);
+        rho_max = fmax(rho_max, sqrt(x * x + y * y));
+      }
+      if (az1 - az0 > M_PI) continue; /* straddles the +-pi cut */
+      const double gx = fmax(fmax(lo[0], -hi[0]), 0.0), gy = fmax(fmax(lo[1], -hi[1]), 0.0);
+      const double rho_min = sqrt(gx * gx + gy * gy);
+      /* elevation atan2(z, rho) grows with z; with rho it falls for z > 0 and grows for z < 0 */
+      const double el1 = atan2(hi[2], hi[2] > 0 ? rho_min : rho_max);
+      const double el0 = atan2(lo[2], lo[2] > 0 ? rho_max : rho_min);
+      const double eps = 1e-9;
+      ba[0] = az0 - eps, ba[1] = el0 - eps, ba[2] = az1 + eps, ba[3] = el1 + eps;
+    }
+  }
   if (nthread < 1) nthread = 1;
   if (nthread > nray) nthread = nray > 0 ? nray : 1;
   multi_job* jobs = (multi_job*)malloc(sizeof(multi_job) * (size_t)nthread);
   pthread_t* th = (pthread_t*)malloc(sizeof(pthread_t) * (size_t)nthread);
   for (int t = 0; t < nthread; t++) {
-    multi_job J = {m,    d,      pnt,  vec, elim, bs_c, bs_r2, geomid, dist,
+    multi_job J = {m,       d,        pnt,      vec,       elim,   cull,  bs_c,
+                   bs_r2,   body_ba,  body_on,  body_adr,  body_geom, geomid, dist,
                    (int)((long long)nray * t / nthread), (int)((long long)nray * (t + 1) / nthread),
                    cutoff};
     jobs[t] = J;
@@ -646,6 +784,17 @@ void orc_multi_ray(const orc_model* m, const orc_data* d, const double pnt[3], c
   free(elim);
   free(bs_c);
   free(bs_r2);
+  free(body_ba);
+  free(body_on);
+  free(body_adr);
+  free(body_geom);
+}
+
+void orc_multi_ray(const orc_model* m, const orc_data* d, const double pnt[3], const double* vec,
+                   const uint8_t* geomgroup, uint8_t flg_static, int bodyexclude, int32_t* geomid,
+                   double* dist, int nray, double cutoff, int nthread) {
+  orc_multi_ray_cull(m, d, pnt, vec, geomgroup, flg_static, bodyexclude, geomid, dist, nray, cutoff,
+                     nthread, ORC_CULL_BODY_ANGULAR);
 }
 
 /* ------------------------------------------------------------------------------------------
@@ -718,6 +867,37 @@ void orc_lidar_scan(const orc_model* m, const orc_data* d, const double sensor_p
   }
   free(jobs);
   free(th);
+}
+
+/* The same scan computed the mj_multiRay way: all rays of the scan share the origin, so the cull
+ * of orc_multi_ray_cull is prepared once per scan; then the rangefinder cutoff and the LaserScan
+ * cast / filter as in orc_lidar_scan.  Results are identical to orc_lidar_scan. */
+void orc_lidar_scan_multiray(const orc_model* m, const orc_data* d, const double sensor_pos[3],
+                             const double sensor_mat[9], const double* local_dir, int nray,
+                             const uint8_t* geomgroup, uint8_t flg_static, int bodyexclude,
+                             double cutoff, double range_min, double range_max, float* ranges,
+                             int32_t* geomid, double* dist_raw, int nthread, int cull) {
+  double* vec = (double*)calloc(3 * ((size_t)nray + 1), sizeof(double));
+  double* dist = (double*)calloc((size_t)nray + 1, sizeof(double));
+  const double* R = sensor_mat;
+  for (int i = 0; i < nray; i++) {
+    const double* l = local_dir + 3 * (size_t)i;
+    vec[3 * (size_t)i + 0] = R[0] * l[0] + R[1] * l[1] + R[2] * l[2];
+    vec[3 * (size_t)i + 1] = R[3] * l[0] + R[4] * l[1] + R[5] * l[2];
+    vec[3 * (size_t)i + 2] = R[6] * l[0] + R[7] * l[1] + R[8] * l[2];
+  }
+  orc_multi_ray_cull(m, d, sensor_pos, vec, geomgroup, flg_static, bodyexclude, geomid, dist, nray,
+                     INFINITY, nthread, cull);
+  for (int i = 0; i < nray; i++) {
+    double val = dist[i];
+    if (cutoff > 0 && val > cutoff) val = cutoff;
+    if (dist_raw) dist_raw[i] = val;
+    float r = (float)val;
+    r = (float)((r < range_min || r > range_max) ? -1.0 : r);
+    ranges[i] = r;
+  }
+  free(vec);
+  free(dist);
 }
 
 /* ref:src/mujoco_lidar.cpp:92-93 */

@@ -105,6 +105,15 @@ void orc_multi_ray(const orc_model* m, const orc_data* d, const double pnt[3], c
                    const uint8_t* geomgroup, uint8_t flg_static, int bodyexclude, int32_t* geomid,
                    double* dist, int nray, double cutoff, int nthread);
 
+/* the same with the cull chosen explicitly (orc_multi_ray = ORC_CULL_BODY_ANGULAR, A.6 as specified) */
+#define ORC_CULL_NONE 0          /* per-ray brute force with precomputed eliminate flags */
+#define ORC_CULL_BODY_ANGULAR 1  /* per-body azimuth / elevation rectangle (A.6) */
+#define ORC_CULL_GEOM_SPHERE 2   /* per-geom bounding sphere vs the ray's line */
+void orc_multi_ray_cull(const orc_model* m, const orc_data* d, const double pnt[3],
+                        const double* vec, const uint8_t* geomgroup, uint8_t flg_static,
+                        int bodyexclude, int32_t* geomid, double* dist, int nray, double cutoff,
+                        int nthread, int cull);
+
 /* ---- A.7 + lidar.cpp:256-271 --------------------------------------------------------------
  * One scan: world dir i = sensor_mat * local_dir[i], origin sensor_pos; mj_ray(geomgroup,
  * flg_static, bodyexclude); rangefinder cutoff (min(cutoff, v) when cutoff > 0); float cast;
@@ -114,6 +123,12 @@ void orc_lidar_scan(const orc_model* m, const orc_data* d, const double sensor_p
                     const uint8_t* geomgroup, uint8_t flg_static, int bodyexclude, double cutoff,
                     double range_min, double range_max, float* ranges, int32_t* geomid,
                     double* dist_raw, int nthread);
+/* the same scan through orc_multi_ray_cull (one origin per scan): identical results */
+void orc_lidar_scan_multiray(const orc_model* m, const orc_data* d, const double sensor_pos[3],
+                             const double sensor_mat[9], const double* local_dir, int nray,
+                             const uint8_t* geomgroup, uint8_t flg_static, int bodyexclude,
+                             double cutoff, double range_min, double range_max, float* ranges,
+                             int32_t* geomid, double* dist_raw, int nthread, int cull);
 /* lidar.cpp:92-93 */
 int orc_lidar_num_rangefinders(double min_angle, double max_angle, double angle_increment);
 

@@ -69,6 +69,13 @@ def lib():
         L.orc_multi_ray.restype = None
         L.orc_multi_ray.argtypes = [C.POINTER(_OrcModel), C.POINTER(_OrcData), _f64p, _f64p, _u8p,
                                     C.c_uint8, C.c_int, _i32p, _f64p, C.c_int, C.c_double, C.c_int]
+        L.orc_multi_ray_cull.restype = None
+        L.orc_multi_ray_cull.argtypes = L.orc_multi_ray.argtypes + [C.c_int]
+        L.orc_lidar_scan_multiray.restype = None
+        L.orc_lidar_scan_multiray.argtypes = [C.POINTER(_OrcModel), C.POINTER(_OrcData), _f64p, _f64p,
+                                              _f64p, C.c_int, _u8p, C.c_uint8, C.c_int, C.c_double,
+                                              C.c_double, C.c_double, _f32p, _i32p, _f64p, C.c_int,
+                                              C.c_int]
         L.orc_lidar_scan.restype = None
         L.orc_lidar_scan.argtypes = [C.POINTER(_OrcModel), C.POINTER(_OrcData), _f64p, _f64p, _f64p,
                                      C.c_int, _u8p, C.c_uint8, C.c_int, C.c_double, C.c_double,
@@ -96,6 +103,9 @@ def _p(a, t):
 
 def _c(a, dt):
     return np.ascontiguousarray(a, dtype=dt)
+
+
+CULL_NONE, CULL_BODY_ANGULAR, CULL_GEOM_SPHERE = 0, 1, 2
 
 
 class OracleScene:
@@ -173,6 +183,33 @@ class OracleScene:
                             _p(gg, _u8p), flg_static, bodyexclude, _p(gid, _i32p), _p(dist, _f64p),
                             n, cutoff, nthread)
         return dist, gid
+
+    def multi_ray_cull(self, pnt, vec, cull, geomgroup=None, flg_static=1, bodyexclude=-1, cutoff=1e10,
+                       nthread=1):
+        """orc_multi_ray with the cull chosen: CULL_NONE / CULL_BODY_ANGULAR / CULL_GEOM_SPHERE."""
+        pnt, vec = _c(pnt, np.float64), _c(vec, np.float64).reshape(-1, 3)
+        n = vec.shape[0]
+        gg = None if geomgroup is None else _c(geomgroup, np.uint8)
+        gid = np.empty(n, np.int32)
+        dist = np.empty(n, np.float64)
+        lib().orc_multi_ray_cull(C.byref(self._m), C.byref(self._d), _p(pnt, _f64p), _p(vec, _f64p),
+                                 _p(gg, _u8p), flg_static, bodyexclude, _p(gid, _i32p),
+                                 _p(dist, _f64p), n, cutoff, nthread, int(cull))
+        return dist, gid
+
+    def lidar_scan_multiray(self, spec, sensor_pos, sensor_mat, cull=1, nthread=1):
+        """lidar_scan computed the mj_multiRay way (one cull preparation per scan)."""
+        pos, mat = _c(sensor_pos, np.float64).reshape(3), _c(sensor_mat, np.float64).reshape(9)
+        n = spec.nray
+        ranges = np.empty(n, np.float32)
+        gid = np.empty(n, np.int32)
+        raw = np.empty(n, np.float64)
+        lib().orc_lidar_scan_multiray(C.byref(self._m), C.byref(self._d), _p(pos, _f64p), _p(mat, _f64p),
+                                      _p(spec.local_dir, _f64p), n, _p(spec.geomgroup, _u8p),
+                                      spec.flg_static, spec.bodyexclude, spec.cutoff, spec.range_min,
+                                      spec.range_max, _p(ranges, _f32p), _p(gid, _i32p),
+                                      _p(raw, _f64p), nthread, int(cull))
+        return ranges, gid, raw
 
     # ---- rangefinder + MujocoLidar::update -----------------------------------------------------
     def lidar_scan(self, spec, sensor_pos, sensor_mat, nthread=1):

@@ -76,6 +76,8 @@ def lib():
         L.b2p_camera_set_gl_depth.argtypes = [C.c_void_p, C.c_void_p]
         L.b2p_camera_rgb.restype = C.c_int
         L.b2p_camera_rgb.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+        L.b2p_refresh_stress.restype = C.c_int
+        L.b2p_refresh_stress.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_double, C.c_void_p]
         L.b2p_sizeof_mjmodel.restype = C.c_size_t
         L.b2p_sizeof_mjdata.restype = C.c_size_t
         assert L.b2p_sizeof_mjmodel() == C.sizeof(MjModel), "mjModel stand-in layout drifted"
@@ -190,6 +192,15 @@ class PluginHarness:
 
     def run_threads(self, ms: int) -> int:
         return self.L.b2p_run_threads(self.h, ms)
+
+    def refresh_stress(self, n_el=64, n_az=2048, hz=1500.0, seconds=2.0) -> dict:
+        """physics-thread refresh at `hz` while a sensor thread casts back to back (test_api.cpp)"""
+        out = np.zeros(5, np.float64)
+        rc = self.L.b2p_refresh_stress(self.h, n_el, n_az, hz, seconds, out.ctypes.data)
+        if rc != 0:
+            raise RuntimeError(f"b2p_refresh_stress {rc}: {self.error()}")
+        return {"p50_us": out[0], "p99_us": out[1], "max_us": out[2], "casts": int(out[3]),
+                "refreshes": int(out[4])}
 
     def lidar_info(self, k=0) -> dict:
         n = C.c_int()

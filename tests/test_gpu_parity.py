@@ -282,12 +282,24 @@ def test_render_depth_roundtrip(oracle, clutter, clutter_gpu):
     vs, us = np.meshgrid(np.arange(48), np.arange(64), indexing="ij")
     l = np.stack([(us + 0.5 - K[2]) / K[0], -(vs + 0.5 - K[5]) / K[4], -np.ones_like(us, float)], -1).reshape(-1, 3)
     vec = l @ R.T
-    d, g = o.multi_ray(pos[0], vec, nthread=8)
+    # the renderer draws what mjv_defaultOption shows (ref:src/mujoco_cameras.cpp:165): groups 0-2
+    d, g = o.multi_ray(pos[0], vec, geomgroup=[1, 1, 1, 0, 0, 0], nthread=8)
     d = d.reshape(48, 64)
     near = (d > 0) & (d < 10)
     assert near.sum() > 500
     np.testing.assert_allclose(z[near], d[near], rtol=2e-4)
     assert np.all(z[d < 0] > 49.9)   # misses sit on the far plane
+    # an explicit mask (all six groups) shows the hidden geoms as well
+    cam_all = engine.DepthCamera(scenes.CameraSpec(64, 48, 58.0, 0.01, 50.0, 1.0, 12, geomgroup=(1,) * 6),
+                                 scene=clutter_gpu)
+    cam_all.render_depth_device(1, d_pos, d_mat, gl)
+    cam_all.depth_to_cloud_device(1, gl, depth, None)
+    clutter_gpu.sync()
+    z_all = depth.cpu().numpy()[0]
+    d_all = o.multi_ray(pos[0], vec, nthread=8)[0].reshape(48, 64)
+    near = (d_all > 0) & (d_all < 10)
+    np.testing.assert_allclose(z_all[near], d_all[near], rtol=2e-4)
+    assert (d_all != d).any()        # groups 3-5 do occlude something in this view
 
 
 def test_empty_and_tiny_scenes():

@@ -212,6 +212,46 @@ def test_multiray_equals_ray_loop(oracle):
     assert np.array_equal(d2[~far], d[~far])
 
 
+def test_multiray_culls_leave_the_result_unchanged(oracle):
+    """mj_multiRay's per-body azimuth / elevation rectangle (and the per-geom
+    bounding-sphere cull) are pure accelerators -- every variant must return mj_ray's answer, from
+    origins inside and outside bodies' boxes, with masks and a cutoff, and on a scene whose bodies
+    are compact (one object per body: the cull really prunes) as well as scattered (clutter500)."""
+    cs = scenes.clutter500(n_el=16, n_az=128)
+    o = oracle.OracleScene(cs.model, cs.poses)
+    rng = np.random.default_rng(3)
+    origins = [cs.sensor_pos, np.array([7.0, -3.0, 0.4]), np.array([-15.0, 12.0, 5.5]),
+               cs.poses.geom_xpos[0, 40] + 0.01]  # the last one sits inside a geom
+    vec = np.concatenate([cs.lidar.local_dir[::5], rng.normal(size=(300, 3)),
+                          [[0, 0, 1.0], [0, 0, -1.0], [1.0, 0, 0], [-1.0, 1e-12, 0]]])
+    for pnt in origins:
+        for gg, fs, be, cut in ((None, 1, 63, 1e10), ([1, 0, 1, 1, 0, 0], 0, -1, 1e10), (None, 1, 5, 9.0)):
+            ref = o.multi_ray_cull(pnt, vec, oracle.CULL_NONE, geomgroup=gg, flg_static=fs, bodyexclude=be,
+                                   cutoff=cut)
+            for cull in (oracle.CULL_BODY_ANGULAR, oracle.CULL_GEOM_SPHERE):
+                d, g = o.multi_ray_cull(pnt, vec, cull, geomgroup=gg, flg_static=fs, bodyexclude=be,
+                                        cutoff=cut, nthread=3)
+                assert np.array_equal(d, ref[0]) and np.array_equal(g, ref[1]), (pnt, cull)
+        for i in range(0, vec.shape[0], 37):
+            di, gi = o.ray(pnt, vec[i], bodyexclude=63)
+            d, g = o.multi_ray_cull(pnt, vec[i:i + 1], oracle.CULL_BODY_ANGULAR, bodyexclude=63)
+            assert (di, gi) == (d[0], g[0])
+    # one object per body: arm worlds' fixture bodies are compact, the rectangle prunes there
+    ws = scenes.arm_worlds(nworld=2, n_rays=256)
+    o2 = oracle.OracleScene(ws.model, ws.poses, world=1)
+    for cull in (oracle.CULL_BODY_ANGULAR, oracle.CULL_GEOM_SPHERE):
+        a = o2.lidar_scan_multiray(ws.lidar, ws.sensor_pos[1], ws.sensor_mat[1], cull=cull)
+        b = o2.lidar_scan(ws.lidar, ws.sensor_pos[1], ws.sensor_mat[1])
+        assert all(np.array_equal(x, y) for x, y in zip(a, b))
+    # lidar_scan_multiray == lidar_scan on the cluttered scene incl. cutoff / range filter
+    spec = scenes.LidarSpec(cs.lidar.local_dir, bodyexclude=63, cutoff=12.0, range_min=1.0, range_max=11.0)
+    pos, mat = cs.sensor_poses(2)
+    b = o.lidar_scan(spec, pos[1], mat[1], nthread=2)
+    for cull in (oracle.CULL_NONE, oracle.CULL_BODY_ANGULAR, oracle.CULL_GEOM_SPHERE):
+        a = o.lidar_scan_multiray(spec, pos[1], mat[1], cull=cull, nthread=2)
+        assert all(np.array_equal(x, y) for x, y in zip(a, b))
+
+
 def test_camera_intrinsics_and_depth(oracle):
     """ref:src/mujoco_cameras.cpp:119-124 (f = 1/tan(fovy/2) * H/2) and :222-240."""
     K = oracle.camera_intrinsics(58.0, 1280, 720)
