@@ -228,11 +228,15 @@ def test_camera_hides_collision_groups(oracle):
     l = np.stack([(us + 0.5 - K[2]) / K[0], -(vs + 0.5 - K[5]) / K[4], -np.ones_like(us, float)], -1).reshape(-1, 3)
     vec = l @ cmat.T
     o = oracle.OracleScene(sc.model, poses)
-    g_def = o.multi_ray(cpos, vec, geomgroup=[1, 1, 1, 0, 0, 0])[1].reshape(48, 64)
-    g_all = o.multi_ray(cpos, vec)[1].reshape(48, 64)
-    group3_only = (g_all >= 0) & (g_all != g_def)       # pixels whose nearest geom is a collision geom
-    assert group3_only.sum() > 0
-    assert (z_def[0][group3_only] > z_all[0][group3_only]).all()
+    d_def, g_def = (a.reshape(48, 64) for a in o.multi_ray(cpos, vec, geomgroup=[1, 1, 1, 0, 0, 0]))
+    d_all, g_all = (a.reshape(48, 64) for a in o.multi_ray(cpos, vec))
+    # pixels where a collision-only geom (the sphere) is nearer than anything the renderer draws; the
+    # coincident visual / collision boxes differ in id only, not in depth
+    occluded = (d_all >= 0) & (d_all != d_def)
+    assert occluded.sum() > 0
+    assert (z_def[0][occluded] > z_all[0][occluded]).all()
+    same = ~occluded
+    assert np.array_equal(z_def[0][same], z_all[0][same])
     assert np.array_equal((gl_def[0] < 1.0), (g_def >= 0))
     s.close()
 
