@@ -137,21 +137,6 @@ __device__ __forceinline__ int tile_ray(int tile, int lane, int tiles_x, int til
   return tile * 32 + lane;
 }
 
-// the same without the division: (ty0, tx0) = row / column of the group's first tile, computed once
-// per group; tile t of the group lies t columns further, wrapping into the next tile row
-__device__ __forceinline__ int group_tile_ray(int tile0, int ty0, int tx0, int t, int lane, int tiles_x,
-                                              int tile_w) {
-  if (tiles_x > 0) {
-    int ty = ty0, tx = tx0 + t;
-    if (tx >= tiles_x) {
-      tx -= tiles_x;
-      ty++;
-    }
-    return (ty * 4 + (lane >> 3)) * tile_w + tx * 8 + (lane & 7);
-  }
-  return (tile0 + t) * 32 + lane;
-}
-
 // the scan's sensor frame and ray r of it (same arithmetic in K2 and in the mesh kernels)
 template <int MODE>
 __device__ __forceinline__ bool scan_ray(const CastParams& p, int scan, int r, double o[3],
@@ -189,62 +174,12 @@ struct GroupGen {
   const CastParams& p;
   const TileGeom& tg;
   int scan, tile0, lane;
-  int ty0, tx0;  // row / column of tile0 (3-D tiling)
-  __device__ __forceinline__ GroupGen(const CastParams& p_, const TileGeom& tg_, int scan_, int tile0_,
-                                      int lane_)
-      : p(p_), tg(tg_), scan(scan_), tile0(tile0_), lane(lane_) {
-    ty0 = tg.tiles_x > 0 ? tile0 / tg.tiles_x : 0;
-    tx0 = tg.tiles_x > 0 ? tile0 - ty0 * tg.tiles_x : 0;
-  }
   __device__ __forceinline__ bool operator()(int t, double vec[3], int& r) const {
-    const int rr = group_tile_ray(tile0, ty0, tx0, t, lane, tg.tiles_x, p.tile_w);
+    const int rr = tile_ray(tile0 + t, lane, tg.tiles_x, p.tile_w);
     const bool in = rr < p.nray;
     r = in ? rr : -1;
     double o[3], l[3];
     return scan_ray<MODE>(p, scan, in ? rr : 0, o, l, vec) && in;
-  }
-};
-
-// fp32 ray generator of one group for K2a (collect_group only needs conservative directions): the
-// sensor frame is converted once per group; the unnormalised direction of tile t's ray of this lane
-template <int MODE>
-struct GroupGenF {
-  const CastParams& p;
-  const TileGeom& tg;
-  int scan, tile0, lane;
-  float R[9];
-  int ty0, tx0;
-  __device__ __forceinline__ void load_frame() {
-    if (MODE != MODE_MULTIRAY) {
-#pragma unroll
-      for (int k = 0; k < 9; k++) R[k] = (float)__ldg(p.smat + (size_t)scan * 9 + k);
-    }
-    ty0 = tg.tiles_x > 0 ? tile0 / tg.tiles_x : 0;
-    tx0 = tg.tiles_x > 0 ? tile0 - ty0 * tg.tiles_x : 0;
-  }
-  __device__ __forceinline__ bool operator()(int t, float v[3], int& r) const {
-    const int rr = group_tile_ray(tile0, ty0, tx0, t, lane, tg.tiles_x, p.tile_w);
-    const bool in = rr < p.nray;
-    r = in ? rr : -1;
-    if (!in) return false;
-    float l[3];
-    if (MODE == MODE_CAMERA) {
-      const int pv = rr / p.cam_w, pu = rr - pv * p.cam_w;
-      l[0] = (float)(((double)pu + 0.5 - p.cam_cx) / p.cam_f);
-      l[1] = (float)(-((double)pv + 0.5 - p.cam_cy) / p.cam_f);
-      l[2] = -1.0f;
-    } else {
-#pragma unroll
-      for (int k = 0; k < 3; k++) l[k] = (float)__ldg(p.local_dir + (size_t)rr * 3 + k);
-    }
-    if (MODE == MODE_MULTIRAY) {
-      v[0] = l[0], v[1] = l[1], v[2] = l[2];
-    } else {
-      v[0] = R[0] * l[0] + R[1] * l[1] + R[2] * l[2];
-      v[1] = R[3] * l[0] + R[4] * l[1] + R[5] * l[2];
-      v[2] = R[6] * l[0] + R[7] * l[1] + R[8] * l[2];
-    }
-    return v[0] != 0.f || v[1] != 0.f || v[2] != 0.f;
   }
 };
 
@@ -383,7 +318,7 @@ __global__ void __launch_bounds__(kCastThreads, B2_CAST_MINBLOCKS)
     double o[3];
 #pragma unroll
     for (int k = 0; k < 3; k++) o[k] = __ldg(p.spos + (size_t)scan * 3 + k);
-    const GroupGen<MODE> gen(p, tg, scan, tile0, lane);
+    const GroupGen<MODE> gen{p, tg, scan, tile0, lane};
     const GroupEpi<MODE, SPLIT> epi{p, tg, scan, tile0, lane};
     trace_group<STAGE>(p, wslots, wnodes, elim, pose, nt, o, tcap, warp, gen, epi);
   }
@@ -495,8 +430,7 @@ __global__ void __launch_bounds__(kCastThreads, B2_COLLECT_MINBLOCKS)
     double o[3];
 #pragma unroll
     for (int k = 0; k < 3; k++) o[k] = __ldg(p.spos + (size_t)scan * 3 + k);
-    GroupGenF<MODE> gen{p, tg, scan, tile0, lane, {}, 0, 0};
-    gen.load_frame();
+    const GroupGen<MODE> gen{p, tg, scan, tile0, lane};
     const int gid = scan * tg.groups_per_scan + tile0 / tg.group_tiles;
     const int n = collect_group<STAGE>(p, wslots, wnodes, elim, pose, nt, o, tcap, warp, gen,
                                        p.cl.list + (size_t)gid * kCandCap);
@@ -552,7 +486,7 @@ __global__ void __launch_bounds__(kCastThreads, B2_DRAIN_MINBLOCKS)
     double o[3];
 #pragma unroll
     for (int k = 0; k < 3; k++) o[k] = __ldg(p.spos + (size_t)scan * 3 + k);
-    const GroupGen<MODE> gen(p, tg, scan, tile0, lane);
+    const GroupGen<MODE> gen{p, tg, scan, tile0, lane};
     GroupEpi<MODE, SPLIT> epi{p, tg, scan, tile0, lane};
 #if B2_DRAIN_STAGED
     __syncwarp();  // the previous group's tiles are done with ca / cb
@@ -602,7 +536,7 @@ __global__ void __launch_bounds__(kCastThreads, B2_CAST_MINBLOCKS)
     double o[3];
 #pragma unroll
     for (int k = 0; k < 3; k++) o[k] = __ldg(p.spos + (size_t)scan * 3 + k);
-    const GroupGen<MODE> gen(p, tg, scan, tile0, lane);
+    const GroupGen<MODE> gen{p, tg, scan, tile0, lane};
     const GroupEpi<MODE, SPLIT> epi{p, tg, scan, tile0, lane};
     trace_group<false>(p, p.wslots + (size_t)world * p.nslot, p.wnodes, p.elim,
                        p.pose + (size_t)world * p.ngeom, nt, o, tcap, warp, gen, epi);

@@ -32,111 +32,43 @@ B2_HD CandRef ld_cand(const CandRef* ptr) {
 #endif
 }
 
-// Unbounded planes as the collect phase sees them: unit normal (fp32) and the height of the group's
-// origin above the plane (fp64 once per group, then fp32).  Only their hit can bound the search.
-constexpr int kMaxBoundPlanes = 4;
-struct PlaneBound {
-  float n[kMaxBoundPlanes][3];
-  float h[kMaxBoundPlanes];  // >= 0 (planes the origin is behind are left out)
-  int count;
-};
-
-// Called by all lanes with warp-uniform arguments.
-B2_HD void plane_bounds(const CastParams& p, const uint8_t* elim, const GeomPose* pose,
-                        const double pnt[3], PlaneBound& pb) {
-  pb.count = 0;
-  for (int i = 0; i < p.nplane; i++) {
-    const int g = p.plane_ids[i];
-    if (elim[g]) continue;
-    const GeomStatic gs = ld_gstat(p.gstat + g);
-    if (gs.size[0] > 0 || gs.size[1] > 0) continue;  // a bounded plane may be missed: no bound from it
-    if (pb.count == kMaxBoundPlanes) continue;       // more planes than slots: their bound is simply unused
-    const GeomPose P = ld_pose(pose + g);
-    const double nx = P.mat[2], ny = P.mat[5], nz = P.mat[8];
-    const double h = nx * (pnt[0] - P.pos[0]) + ny * (pnt[1] - P.pos[1]) + nz * (pnt[2] - P.pos[2]);
-    if (!(h >= 0)) continue;  // origin behind the one-sided plane: no ray of the group hits it
-    const double nn = sqrt(nx * nx + ny * ny + nz * nz);
-    if (!(nn > 0.5 && nn < 2.0)) continue;  // not a rotation matrix: no bound
-    const int k = pb.count++;
-    pb.n[k][0] = (float)(nx / nn);
-    pb.n[k][1] = (float)(ny / nn);
-    pb.n[k][2] = (float)(nz / nn);
-    pb.h[k] = (float)(h / nn);
-  }
-}
-
-// Upper bound (world units, squared, rounded up) of how far a ray with fp32 unit direction d (each
-// component within 2e-6 of the true one) can travel before an unbounded plane stops it; cap2 when
-// no plane certainly does.  A plane is hit iff the origin is on its visible side (h >= 0) and the
-// ray descends towards it; D = h / -(n.d).  The bound takes the errors of h (1e-6 relative + 1e-7 of
-// the origin's magnitude) and of n.d (6e-6 absolute) to the far side and is only used when -(n.d)
-// is large against its error.
-B2_HD float plane_far2(const PlaneBound& pb, const float d[3], float omag, float cap2) {
-  float best = cap2;
-  for (int k = 0; k < pb.count; k++) {
-    const float nd = pb.n[k][0] * d[0] + pb.n[k][1] * d[1] + pb.n[k][2] * d[2];
-    const float h = pb.h[k];
-    const float down = -nd - 6e-6f;
-    if (!(down > 2e-5f)) continue;
-    const float hu = h * (1.0f + 2e-6f) + 2e-7f * omag + 1e-30f;
-    const float D = hu / down * (1.0f + 4e-6f);
-    const float D2 = D * D * (1.0f + 4e-6f);
-    best = fminf(best, D2);
-  }
-  return best;
-}
-
 // One group of nt <= kGroupTiles tiles: returns the number of candidates written to out[] (sorted by
 // key2, ties by collect order), or -1 if the fused path must trace the group.
-//   genf(t, v, r) -> bool: the UNNORMALISED fp32 direction of this lane's ray of tile t (each
-//   component within a few ulp of the true double direction); false: no ray here, or a ray whose
-//   direction is exactly zero (it is traced as a miss everywhere).
 //   W supplies: size/lane/ballot/any/popc/lanemask_lt/sync/sum/min/max, queue(), order(),
 //   cand_a() (used as the unit-direction buffer) and cref() (kCandCap staging entries).
-// Everything here is fp32 and only has to be CONSERVATIVE: the cone must contain every ray of the
-// group and far2 must not undercut any ray's search distance; the distances themselves are decided
-// by K2b in fp64.  (The fp64 ray generation and plane tests this phase used to repeat for all 128
-// rays were a third of K2a's instructions.)
-template <bool STAGE, class W, class GenF>
+template <bool STAGE, class W, class Gen>
 B2_HD int collect_group(const CastParams& p, const WideChild* wslots, const WideNode* wnodes,
                         const uint8_t* elim, const GeomPose* pose, int nt, const double pnt[3],
-                        float tcap, W& warp, const GenF& genf, CandRef* out) {
+                        float tcap, W& warp, const Gen& gen, CandRef* out) {
   const int L = warp.size(), lane = warp.lane();
   int32_t* queue = warp.queue();
   int32_t* order = warp.order();
   CandRef* cref = warp.cref();
   float* dfbuf = reinterpret_cast<float*>(warp.cand_a());
 
-  PlaneBound pb;
-  plane_bounds(p, elim, pose, pnt, pb);
-  const float omag = fabsf((float)pnt[0]) + fabsf((float)pnt[1]) + fabsf((float)pnt[2]);
-
-  // ---- A'. unit directions, cone sums and the far bound ------------------------------------------
+  // ---- A'. rays and planes, as far as the cone and the far bound need them ---------------------
   float sx = 0.f, sy = 0.f, sz = 0.f, lim2max = 0.f;
   bool odd = false, any_active = false;
   for (int t = 0; t < nt; t++) {
-    float v[3];
+    double vec[3];
     int r = -1;
-    const bool active = genf(t, v, r);
-    float df[3] = {0.f, 0.f, 0.f};
+    const bool active = gen(t, vec, r);
+    Hit hit;
+    hit.dist = -1;
+    hit.id = -1;
+    for (int i = 0; i < p.nplane; i++) {
+      const int g = p.plane_ids[i];
+      if (elim[g]) continue;
+      if (active)
+        hit_update(hit, plane_test(pose + g, p.gstat + g, pnt, vec), g);
+    }
+    float df[3] = {0.f, 0.f, 0.f}, vlen_up = 0.f;
     if (active) {
-      const float s2 = v[0] * v[0] + v[1] * v[1] + v[2] * v[2];
-      if (s2 > 1e-28f && s2 < 1e28f) {
-        const float inv = rsqrt_f32(s2);
-        df[0] = v[0] * inv;
-        df[1] = v[1] * inv;
-        df[2] = v[2] * inv;
-        // search limit in world units: the plane bound, or tcap * |vec| (rounded up)
-        float cap2 = INFINITY;
-        if (tcap < FLT_MAX) {
-          const float lim = tcap * (s2 * inv) * (1.0f + 8e-6f);
-          cap2 = lim * lim * (1.0f + 1e-6f);
-        }
-        // (a plane's one-sidedness is decided on the unnormalised direction against mjMINVAL: the
-        // unit-direction test above only implies it while |vec| is not tiny)
-        lim2max = fmaxf(lim2max, s2 > 1e-12f ? plane_far2(pb, df, omag, cap2) : cap2);
+      if (unit_dir(vec, df, vlen_up)) {
+        lim2max = fmaxf(lim2max, lane_lim2(hit, tcap, vlen_up));
       } else {
-        odd = true;  // outside the float range (or too close to zero to classify): fused path
+        df[0] = df[1] = df[2] = 0.f;
+        odd = true;
       }
     }
     sx += df[0];
@@ -167,9 +99,9 @@ B2_HD int collect_group(const CastParams& p, const WideChild* wslots, const Wide
     if (has) cmin = fminf(cmin, d[0] * tc.a[0] + d[1] * tc.a[1] + d[2] * tc.a[2]);
   }
   cmin = warp.min(cmin);
-  tc.cos_t = fminf(fmaxf(cmin - 1.6e-5f, -1.0f), 1.0f);  // fp32 unit directions: 2e-6 per component
+  tc.cos_t = fminf(fmaxf(cmin - 8e-6f, -1.0f), 1.0f);
   if (tc.cos_t < 0.2f) tc.wide = true;
-  tc.sin_t = sqrtf(fmaxf(1.0f - tc.cos_t * tc.cos_t, 0.f)) + 1.6e-5f;
+  tc.sin_t = sqrtf(fmaxf(1.0f - tc.cos_t * tc.cos_t, 0.f)) + 8e-6f;
   tc.omag = 0.f;
 #pragma unroll
   for (int k = 0; k < 3; k++) {

@@ -178,22 +178,8 @@ void run(const EmuScene& S, CastParams& p, const double o[3], const double* R) {
     // per tile, with the fused trace_group for the groups the single collect pass gives up on
     if (two) {
       CandRef list[kCandCap];
-      // the collect phase sees fp32 directions (cast_kernels.cu GroupGenF)
-      auto genf = [&](int t, float v[3], int& r) {
-        double l[3], vec[3];
-        r = r0 + t;
-        cast_make_ray(p, p.mode, R, r, l, vec);
-        if (p.mode == MODE_MULTIRAY) {
-          v[0] = (float)vec[0], v[1] = (float)vec[1], v[2] = (float)vec[2];
-        } else {
-          float Rf[9], lf[3] = {(float)l[0], (float)l[1], (float)l[2]};
-          for (int k = 0; k < 9; k++) Rf[k] = (float)R[k];
-          for (int k = 0; k < 3; k++) v[k] = Rf[3 * k] * lf[0] + Rf[3 * k + 1] * lf[1] + Rf[3 * k + 2] * lf[2];
-        }
-        return v[0] != 0.f || v[1] != 0.f || v[2] != 0.f;
-      };
       const int n = collect_group<false>(p, p.wslots, p.wnodes, p.elim, p.pose, nt, o, tcap, warp,
-                                         genf, list);
+                                         gen, list);
       if (n >= 0) {
         // staged (the device's default) and unstaged candidate access, alternating per group
         const bool staged = ((r0 / kGroupTiles) & 1) == 0;
@@ -273,36 +259,6 @@ int emu_lidar(const b2_model_desc* m, const double* xpos, const double* xmat,
 }
 
 long long emu_fallbacks() { return g_emu_fallbacks; }
-
-// K2a's fp32 search bound from unbounded planes (split_trace.cuh plane_bounds / plane_far2) for n
-// rays from one origin against ONE plane geom: out[i] = squared world distance bound (inf: none)
-void emu_plane_far2(const double pnt[3], const double* vec, int n, const double ppos[3],
-                    const double pmat[9], const double psize[3], float* out) {
-  GeomPose P;
-  GeomStatic gs{};
-  for (int k = 0; k < 3; k++) P.pos[k] = ppos[k], gs.size[k] = psize[k];
-  for (int k = 0; k < 9; k++) P.mat[k] = pmat[k];
-  gs.type = GEOM_PLANE;
-  const int32_t plane_id = 0;
-  const uint8_t elim = 0;
-  CastParams p{};
-  p.nplane = 1;
-  p.plane_ids = &plane_id;
-  p.gstat = &gs;
-  PlaneBound pb;
-  plane_bounds(p, &elim, &P, pnt, pb);
-  const float omag = fabsf((float)pnt[0]) + fabsf((float)pnt[1]) + fabsf((float)pnt[2]);
-  for (int i = 0; i < n; i++) {
-    float v[3] = {(float)vec[3 * i], (float)vec[3 * i + 1], (float)vec[3 * i + 2]};
-    const float s2 = v[0] * v[0] + v[1] * v[1] + v[2] * v[2];
-    out[i] = INFINITY;
-    if (s2 > 1e-12f && s2 < 1e28f) {
-      const float inv = rsqrt_f32(s2);
-      const float d[3] = {v[0] * inv, v[1] * inv, v[2] * inv};
-      out[i] = plane_far2(pb, d, omag, INFINITY);
-    }
-  }
-}
 
 // the sign-only bounding-sphere pre-test: out[i] = sphere_miss(pos, r*r, pnt, vec)
 void emu_sphere_miss_batch(int n, const double* pos, const double* radius, const double* pnt,

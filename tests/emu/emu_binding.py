@@ -50,23 +50,10 @@ def lib():
                                     C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int64)]
         L.emu_prim_batch.restype = None
         L.emu_prim_batch.argtypes = [C.c_int] + [C.c_void_p] * 7
-        L.emu_plane_far2.restype = None
-        L.emu_plane_far2.argtypes = [C.c_void_p, C.c_void_p, C.c_int] + [C.c_void_p] * 4
         L.emu_sphere_miss_batch.restype = None
         L.emu_sphere_miss_batch.argtypes = [C.c_int] + [C.c_void_p] * 5
         _lib = L
     return _lib
-
-
-def plane_far2(pnt, vec, ppos, pmat, psize) -> np.ndarray:
-    """K2a's fp32 search bound (squared world distance, inf = none) of n rays against one plane."""
-    a = [np.ascontiguousarray(x, np.float64) for x in (pnt, vec, ppos, pmat, psize)]
-    n = a[1].reshape(-1, 3).shape[0]
-    out = np.empty(n, np.float32)
-    lib().emu_plane_far2(C.c_void_p(a[0].ctypes.data), C.c_void_p(a[1].ctypes.data), n,
-                         C.c_void_p(a[2].ctypes.data), C.c_void_p(a[3].ctypes.data),
-                         C.c_void_p(a[4].ctypes.data), C.c_void_p(out.ctypes.data))
-    return out
 
 
 def sphere_miss_batch(pos, radius, pnt, vec) -> np.ndarray:
