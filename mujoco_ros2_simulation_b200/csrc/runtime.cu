@@ -337,8 +337,11 @@ void cast_shape(const b2_scene* s, const CastParams& p, bool& stage, int& tiles_
   const int warps = cast_threads_per_block() / 32;
   const long long tiles = (long long)cast_tiles_per_scan(p.nray) * p.nscan;
   const long long want_blocks = (long long)s->sm_count * 16;
-  // a warp walks groups of 4 tiles: the unit of work of a CTA is warps * 4 tiles
-  const int unit = warps * 4;
+  // a warp walks groups of g tiles (4, or fewer for coarse sensors and small launches): the unit of
+  // work of a CTA is warps * g tiles.  (A single 64x2048 scan with g = 1 used to get 128 CTAs of 32
+  // tiles -- less than one CTA per SM; with the unit following g it gets 512 CTAs of 8.)
+  const int g = (p.group_tiles == 1 || p.group_tiles == 2) ? p.group_tiles : 4;
+  const int unit = warps * g;
   long long tpb = tiles / want_blocks;
   tpb = (tpb / unit) * unit;
   if (tpb < unit) tpb = unit;
