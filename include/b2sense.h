@@ -120,6 +120,7 @@ const char* b2_last_error(void);
  * that update does not cover start as copies of it) and refit on every later update.  stream: a cudaStream_t to enqueue on, or NULL for an internal one. */
 int b2_scene_create(const b2_model_desc* model, int32_t nworld, int32_t device, void* stream,
                     b2_scene** out);
+/* fails with B2_ERR_INVALID while lidars / cameras created on the scene are still alive */
 int b2_scene_destroy(b2_scene* scene);
 
 /* Per-step pose refresh: mjData geom_xpos [nworld*ngeom*3] / geom_xmat [nworld*ngeom*9] for

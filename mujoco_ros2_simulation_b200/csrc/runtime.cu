@@ -136,6 +136,7 @@ struct b2_scene {
     bool upload_pending = false;
   } pm;
   int topo_version = 0;  // bumped by every topology (re)build: invalidates captured graphs
+  std::atomic<int> dependents{0};  // live lidars / cameras bound to this scene
   // scratch of the split mesh path (sized for one chunk of rays)
   DevBuf<int32_t> d_pair_slot, d_pair_geom, d_aff_prim_id, d_aff_mesh_id, d_counters;
   DevBuf<double> d_pair_x;
@@ -203,6 +204,7 @@ struct b2_lidar {
   double last_device_us = 0.0;  // device time of the last host cast (first enqueue .. last kernel)
   HostCast pend;
   LidarGraph graph;
+  bool counted = false;  // registered in scene->dependents
 };
 
 struct b2_camera {
@@ -610,6 +612,8 @@ int b2_scene_create(const b2_model_desc* m, int32_t nworld, int32_t device, void
 
 int b2_scene_destroy(b2_scene* s) {
   if (!s) return B2_OK;
+  if (s->dependents.load() > 0)
+    return fail(B2_ERR_INVALID, "b2_scene_destroy: lidars / cameras of this scene are still alive");
   cudaSetDevice(s->device);
   if (s->stream) cudaStreamSynchronize(s->stream);
   if (s->copy_stream) {
@@ -976,6 +980,8 @@ int b2_lidar_create(b2_scene* s, const b2_lidar_desc* d, b2_lidar** out) {
     b2_lidar_destroy(l);
     return fail(B2_ERR_CUDA, std::string("b2_lidar_create: ") + cudaGetErrorString(e));
   }
+  s->dependents++;
+  l->counted = true;
   *out = l;
   return B2_OK;
 }
@@ -1003,6 +1009,7 @@ int b2_lidar_destroy(b2_lidar* l) {
   if (l->graph.exec) cudaGraphExecDestroy(l->graph.exec);
   if (l->cast_t0) cudaEventDestroy(l->cast_t0);
   if (l->cast_t1) cudaEventDestroy(l->cast_t1);
+  if (l->counted) l->scene->dependents--;
   delete l;
   return B2_OK;
 }
@@ -1495,6 +1502,7 @@ int b2_camera_create(b2_scene* scene, int32_t device, const b2_camera_desc* d, b
   c->near_f = (float)(d->znear * d->extent);
   c->far_f = (float)(d->zfar * d->extent);
   c->depth_scale = 1.0f - c->near_f / c->far_f;
+  if (scene) scene->dependents++;
   *out = c;
   return B2_OK;
 }
@@ -1514,6 +1522,7 @@ int b2_camera_destroy(b2_camera* c) {
   c->h_out.release();
   if (c->done) cudaEventDestroy(c->done);
   if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
+  if (c->scene) c->scene->dependents--;
   delete c;
   return B2_OK;
 }

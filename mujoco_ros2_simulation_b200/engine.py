@@ -8,6 +8,7 @@ block.  All compute happens in libb2sense.so's CUDA kernels; there is no Python 
 from __future__ import annotations
 
 import ctypes as C
+import weakref
 
 import numpy as np
 
@@ -67,10 +68,15 @@ class Scene:
         _capi.check(self.lib.b2_scene_create(C.byref(desc), self.nworld, self.device,
                                              C.c_void_p(stream) if stream else None, C.byref(h)))
         self._h = h
+        self._children = weakref.WeakSet()  # lidars / cameras bound to this scene
 
     def close(self):
+        """Destroys the scene; lidars and cameras still bound to it are closed first (the C ABI
+        refuses to destroy a scene with live dependents)."""
         if getattr(self, "_h", None):
-            self.lib.b2_scene_destroy(self._h)
+            for child in list(self._children):
+                child.close()
+            _capi.check(self.lib.b2_scene_destroy(self._h))
             self._h = None
 
     def __del__(self):
@@ -140,6 +146,7 @@ class Lidar:
         h = C.c_void_p()
         _capi.check(self.lib.b2_lidar_create(scene._h, C.byref(d), C.byref(h)))
         self._h = h
+        scene._children.add(self)
 
     def close(self):
         if getattr(self, "_h", None):
@@ -249,6 +256,8 @@ class DepthCamera:
         _capi.check(self.lib.b2_camera_create(scene._h if scene else None, device, C.byref(d),
                                               C.byref(h)))
         self._h = h
+        if scene is not None:
+            scene._children.add(self)
 
     def close(self):
         if getattr(self, "_h", None):
