@@ -245,6 +245,13 @@ int b2_peer_buffer_create(int32_t device, size_t bytes, void** d_ptr,
  * B2_ERR_CUDA when the two GPUs are not P2P-connected or the handle is stale */
 int b2_peer_buffer_open(int32_t device, const uint8_t handle[B2_PEER_HANDLE_BYTES], void** d_ptr);
 int b2_peer_buffer_close(int32_t device, void* d_ptr);   /* a pointer from _open  */
+/* Bulk form of the gather: copy `bytes` of device memory (e.g. a finished block of results) to
+ * another device pointer (e.g. a slice of a peer buffer) with the copy engine, on the scene's copy
+ * stream, ordered after everything enqueued on the scene's stream so far -- the traversal of the
+ * next block keeps all SMs while the block crosses NVLink.  b2_scene_join makes the scene's stream
+ * wait for the copies enqueued so far (b2_scene_sync waits for both on the host). */
+int b2_scene_copy_async(b2_scene* scene, void* d_dst, const void* d_src, size_t bytes);
+int b2_scene_join(b2_scene* scene);
 int b2_peer_buffer_destroy(int32_t device, void* d_ptr); /* a pointer from _create */
 
 /* ---- introspection used by bench.py / tests ------------------------------------------------ */

@@ -137,6 +137,7 @@ struct b2_scene {
   } pm;
   int topo_version = 0;  // bumped by every topology (re)build: invalidates captured graphs
   std::atomic<int> dependents{0};  // live lidars / cameras bound to this scene
+  cudaEvent_t copy_fork = nullptr, copy_join = nullptr;  // b2_scene_copy_async / b2_scene_join
   // scratch of the split mesh path (sized for one chunk of rays)
   DevBuf<int32_t> d_pair_slot, d_pair_geom, d_aff_prim_id, d_aff_mesh_id, d_counters;
   DevBuf<double> d_pair_x;
@@ -654,6 +655,8 @@ int b2_scene_destroy(b2_scene* s) {
     if (s->stage_done[i]) cudaEventDestroy(s->stage_done[i]);
     if (s->refit_done[i]) cudaEventDestroy(s->refit_done[i]);
   }
+  if (s->copy_fork) cudaEventDestroy(s->copy_fork);
+  if (s->copy_join) cudaEventDestroy(s->copy_join);
   for (int i = 0; i < 3; i++) s->pm.slot[i].release();
   if (s->pm.upload_done) cudaEventDestroy(s->pm.upload_done);
   if (s->own_stream && s->stream) cudaStreamDestroy(s->stream);
@@ -1796,6 +1799,29 @@ int b2_peer_buffer_open(int32_t device, const uint8_t* handle, void** d_ptr) {
   void* p = nullptr;
   B2_CUDA(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
   *d_ptr = p;
+  return B2_OK;
+}
+
+int b2_scene_copy_async(b2_scene* s, void* d_dst, const void* d_src, size_t bytes) {
+  if (!s) return fail(B2_ERR_INVALID, "null scene");
+  if (bytes == 0) return B2_OK;
+  if (!d_dst || !d_src) return fail(B2_ERR_INVALID, "b2_scene_copy_async: null pointer");
+  std::lock_guard<std::recursive_mutex> lock(s->mtx);
+  B2_CUDA(cudaSetDevice(s->device));
+  if (!s->copy_fork) B2_CUDA(cudaEventCreateWithFlags(&s->copy_fork, cudaEventDisableTiming));
+  B2_CUDA(cudaEventRecord(s->copy_fork, s->stream));
+  B2_CUDA(cudaStreamWaitEvent(s->copy_stream, s->copy_fork, 0));
+  B2_CUDA(cudaMemcpyAsync(d_dst, d_src, bytes, cudaMemcpyDefault, s->copy_stream));
+  return B2_OK;
+}
+
+int b2_scene_join(b2_scene* s) {
+  if (!s) return fail(B2_ERR_INVALID, "null scene");
+  std::lock_guard<std::recursive_mutex> lock(s->mtx);
+  B2_CUDA(cudaSetDevice(s->device));
+  if (!s->copy_join) B2_CUDA(cudaEventCreateWithFlags(&s->copy_join, cudaEventDisableTiming));
+  B2_CUDA(cudaEventRecord(s->copy_join, s->copy_stream));
+  B2_CUDA(cudaStreamWaitEvent(s->stream, s->copy_join, 0));
   return B2_OK;
 }
 

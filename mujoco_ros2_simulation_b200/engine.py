@@ -102,6 +102,15 @@ class Scene:
     def sync(self):
         _capi.check(self.lib.b2_scene_sync(self._h))
 
+    def copy_async(self, dst, src, nbytes: int):
+        """copy-engine copy on the scene's copy stream, ordered after the scene's stream (dst / src:
+        device tensors or raw addresses, e.g. a slice of a peer buffer)"""
+        _capi.check(self.lib.b2_scene_copy_async(self._h, _ptr(dst), _ptr(src), int(nbytes)))
+
+    def join(self):
+        """the scene's stream waits for the copies enqueued so far"""
+        _capi.check(self.lib.b2_scene_join(self._h))
+
     def stats(self) -> dict:
         nn, npl = C.c_int32(), C.c_int32()
         mn, mt = C.c_int64(), C.c_int64()

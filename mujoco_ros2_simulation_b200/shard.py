@@ -6,9 +6,12 @@ results over NVLink (BASELINE.json configs[4]).
 cross-GPU traffic is the result gather, in one of two forms:
 
 ``PeerGather``  (the product path)  the gathered arrays live in PEER BUFFERS on the root GPU
-                (``b2_peer_buffer_*``, CUDA IPC); every rank hands the cast kernels a pointer
-                into the root's memory, so the kernels' own float4 / int4 result stores ARE the
-                gather -- they cross NVLink / NVSwitch while the traversal runs.
+                (``b2_peer_buffer_*``, CUDA IPC) that every rank maps.  Two ways to fill them:
+                ``ptr()`` -- hand the cast kernels a pointer into the root's memory, so the
+                kernels' own float4 / int4 result stores ARE the gather; ``push()`` -- cast into
+                local memory block by block and let the copy engine carry each finished block
+                across NVLink while the next one is cast (bulk transfers: the better form when
+                the root's ingress is the limit, i.e. at 8 GPUs).
 ``BlockGather`` (the library baseline, and the CPU test tier over gloo)  the rank's scans are cut
                 into blocks; block k is all-gathered with ``torch.distributed`` on a side
                 stream while block k+1 is being cast.
@@ -205,6 +208,12 @@ class PeerGather:
     def ptr(self, name: str, row: int = 0) -> int:
         """device pointer of row ``row`` of THIS rank's slice of ``name`` (root's memory)"""
         return self.base[name] + (self.rank * self.rows + row) * self.row_bytes(name)
+
+    def push(self, scene, name: str, row: int, src):
+        """Bulk form: copy the finished rows `src` (a contiguous device tensor, rows [row, row + n) of
+        this rank's slice) into the root's buffer with the copy engine, behind the work enqueued on
+        the scene's stream so far (b2_scene_copy_async).  On the root itself it is a local copy."""
+        scene.copy_async(self.ptr(name, row), src, src.numel() * src.element_size())
 
     def root_tensor(self, name: str):
         import torch
