@@ -585,12 +585,56 @@ def measure_gather(ctx, step_ms_sharded: float):
                 dist.barrier()
 
             ms = run(step_push, args.steps)
-            ok = None
-            if rank == 0:
+
+            def verify():
+                if rank != 0:
+                    return None
                 G, Rr = pg.root_tensor("geomid"), pg.root_tensor("ranges")
-                ok = all([int(G[r].to(torch.int64).sum().item()),
-                          int(Rr[r].view(torch.int32).to(torch.int64).sum().item())] ==
-                         [int(v) for v in allsums[r].tolist()] for r in range(world))
+                good = all([int(G[r].to(torch.int64).sum().item()),
+                            int(Rr[r].view(torch.int32).to(torch.int64).sum().item())] ==
+                           [int(v) for v in allsums[r].tolist()] for r in range(world))
+                G.zero_()
+                Rr.zero_()
+                return good
+
+            ok = verify()
+            stream.synchronize()
+            ctx["barrier"]()
+            # the same as a STREAMING loop: results double-buffered on the rank, the tail of step s's
+            # transfers overlaps the first block of step s+1 (b2_scene_copy_fence: one-step lag); the
+            # last step is joined inside the timed region
+            bufs = ((ranges, geomid), (torch.empty_like(ranges), torch.empty_like(geomid)))
+            parity = [0]
+
+            def step_stream():
+                r_, g_ = bufs[parity[0]]
+                parity[0] ^= 1
+                scene.update_poses_device(d_xpos, d_xmat)
+                for lo, hi in blocks:
+                    lidar.cast_device(hi - lo, d_pos[lo:hi], d_mat[lo:hi], d_world[lo:hi], ranges=r_[lo:hi],
+                                      geomid=g_[lo:hi])
+                    pg.push(scene, "ranges", lo, r_[lo:hi])
+                    pg.push(scene, "geomid", lo, g_[lo:hi])
+                scene.copy_fence()
+
+            for _ in range(3):
+                step_stream()
+            scene.join()
+            stream.synchronize()
+            ctx["barrier"]()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            for _ in range(args.steps):
+                step_stream()
+            scene.join()
+            dist.barrier()
+            e1.record(stream)
+            stream.synchronize()
+            torch.cuda.synchronize()
+            ctx["barrier"]()
+            ms_stream = ctx["reduce_max"](e0.elapsed_time(e1)) / args.steps
+            del bufs
+            ok_stream = verify()
             gbytes = (world - 1) * nscan * nray * BYTES_PER_RAY
             out["p2p_copy_blocks"] = {
                 "ms_per_step": ms, "value_with_gather": rays_job / (ms * 1e-3) / 1e9,
@@ -599,6 +643,14 @@ def measure_gather(ctx, step_ms_sharded: float):
                 "verified_checksums": ok,
                 "how": "scan block k is cast into local memory, then the copy engine moves it into rank 0's peer "
                        "buffer (b2_scene_copy_async, bulk NVLink transfers, no SM) while block k+1 is cast"}
+            out["p2p_copy_stream"] = {
+                "ms_per_step": ms_stream, "value_with_gather": rays_job / (ms_stream * 1e-3) / 1e9,
+                "gather_ms": ms_stream - step_ms_sharded, "blocks": len(blocks),
+                "root_ingress_gb_per_step": gbytes / 1e9, "root_ingress_gbs": gbytes / (ms_stream * 1e-3) / 1e9,
+                "verified_checksums": ok_stream,
+                "how": "p2p_copy_blocks as a streaming loop: results double-buffered on the rank, the transfers "
+                       "of step s's last block overlap the first block of step s+1 (b2_scene_copy_fence); the "
+                       "final step is joined inside the timed region"}
             stream.synchronize()
             ctx["barrier"]()
             pg.close()

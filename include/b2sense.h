@@ -252,6 +252,10 @@ int b2_peer_buffer_close(int32_t device, void* d_ptr);   /* a pointer from _open
  * wait for the copies enqueued so far (b2_scene_sync waits for both on the host). */
 int b2_scene_copy_async(b2_scene* scene, void* d_dst, const void* d_src, size_t bytes);
 int b2_scene_join(b2_scene* scene);
+/* One-step-lagged form for a streaming loop with double-buffered sources: marks the copies
+ * enqueued so far as "step s" and makes the scene's stream wait for the copies of step s-1 only, so
+ * the tail of step s's transfers overlaps the first block of step s+1.  Finish with b2_scene_join. */
+int b2_scene_copy_fence(b2_scene* scene);
 int b2_peer_buffer_destroy(int32_t device, void* d_ptr); /* a pointer from _create */
 
 /* ---- introspection used by bench.py / tests ------------------------------------------------ */

@@ -87,6 +87,7 @@ SYMBOLS = {
     "b2_rgb_flip_device": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
     "b2_scene_copy_async": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
     "b2_scene_join": (C.c_int, [C.c_void_p]),
+    "b2_scene_copy_fence": (C.c_int, [C.c_void_p]),
     "b2_peer_buffer_create": (C.c_int, [C.c_int32, C.c_size_t, C.POINTER(C.c_void_p), u8p]),
     "b2_peer_buffer_open": (C.c_int, [C.c_int32, u8p, C.POINTER(C.c_void_p)]),
     "b2_peer_buffer_close": (C.c_int, [C.c_int32, C.c_void_p]),

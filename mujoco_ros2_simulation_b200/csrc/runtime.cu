@@ -138,6 +138,9 @@ struct b2_scene {
   int topo_version = 0;  // bumped by every topology (re)build: invalidates captured graphs
   std::atomic<int> dependents{0};  // live lidars / cameras bound to this scene
   cudaEvent_t copy_fork = nullptr, copy_join = nullptr;  // b2_scene_copy_async / b2_scene_join
+  cudaEvent_t copy_fence[2] = {nullptr, nullptr};        // b2_scene_copy_fence (one-step lag)
+  bool copy_fence_used[2] = {false, false};
+  int copy_fence_flip = 0;
   // scratch of the split mesh path (sized for one chunk of rays)
   DevBuf<int32_t> d_pair_slot, d_pair_geom, d_aff_prim_id, d_aff_mesh_id, d_counters;
   DevBuf<double> d_pair_x;
@@ -657,6 +660,8 @@ int b2_scene_destroy(b2_scene* s) {
   }
   if (s->copy_fork) cudaEventDestroy(s->copy_fork);
   if (s->copy_join) cudaEventDestroy(s->copy_join);
+  for (int i = 0; i < 2; i++)
+    if (s->copy_fence[i]) cudaEventDestroy(s->copy_fence[i]);
   for (int i = 0; i < 3; i++) s->pm.slot[i].release();
   if (s->pm.upload_done) cudaEventDestroy(s->pm.upload_done);
   if (s->own_stream && s->stream) cudaStreamDestroy(s->stream);
@@ -1822,6 +1827,20 @@ int b2_scene_join(b2_scene* s) {
   if (!s->copy_join) B2_CUDA(cudaEventCreateWithFlags(&s->copy_join, cudaEventDisableTiming));
   B2_CUDA(cudaEventRecord(s->copy_join, s->copy_stream));
   B2_CUDA(cudaStreamWaitEvent(s->stream, s->copy_join, 0));
+  return B2_OK;
+}
+
+int b2_scene_copy_fence(b2_scene* s) {
+  if (!s) return fail(B2_ERR_INVALID, "null scene");
+  std::lock_guard<std::recursive_mutex> lock(s->mtx);
+  B2_CUDA(cudaSetDevice(s->device));
+  for (int i = 0; i < 2; i++)
+    if (!s->copy_fence[i]) B2_CUDA(cudaEventCreateWithFlags(&s->copy_fence[i], cudaEventDisableTiming));
+  const int i = s->copy_fence_flip;
+  s->copy_fence_flip ^= 1;
+  B2_CUDA(cudaEventRecord(s->copy_fence[i], s->copy_stream));
+  if (s->copy_fence_used[i ^ 1]) B2_CUDA(cudaStreamWaitEvent(s->stream, s->copy_fence[i ^ 1], 0));
+  s->copy_fence_used[i] = true;
   return B2_OK;
 }
 

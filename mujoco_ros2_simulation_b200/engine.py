@@ -111,6 +111,10 @@ class Scene:
         """the scene's stream waits for the copies enqueued so far"""
         _capi.check(self.lib.b2_scene_join(self._h))
 
+    def copy_fence(self):
+        """streaming loop: mark the copies so far as this step's; wait for the PREVIOUS step's only"""
+        _capi.check(self.lib.b2_scene_copy_fence(self._h))
+
     def stats(self) -> dict:
         nn, npl = C.c_int32(), C.c_int32()
         mn, mt = C.c_int64(), C.c_int64()
