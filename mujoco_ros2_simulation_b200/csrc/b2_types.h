@@ -96,12 +96,18 @@ struct B2_ALIGN(16) MeshTri {
 };
 static_assert(sizeof(MeshTri) == 48, "MeshTri must be 48 B");
 
-struct MeshInfo {
+struct B2_ALIGN(16) MeshInfo {
   int32_t node_base;  // first MeshNode4 of this mesh in the mesh-node array
   int32_t tri_base;   // first MeshTri of this mesh
   int32_t nnode;
   int32_t ntri;
+  // bounding sphere of the mesh's triangles in the mesh frame (centre, radius inflated by 1e-6): a ray
+  // that misses it meets no triangle, so it needs no (ray, mesh) pair -- tighter than the geom_size box
+  // for anything roundish, and decided by sign alone (sphere_miss)
+  float bs_c[3];
+  float bs_r;
 };
+static_assert(sizeof(MeshInfo) == 32, "MeshInfo must be 32 B");
 
 // ray generation modes of the cast kernel
 enum CastMode : int32_t {

@@ -100,6 +100,9 @@ struct DevWarp {
     // mj_rayMesh's own pre-test (ray vs the geom_size box, fp64): a ray that misses it returns -1
     // upstream, so it needs no pair.  Roughly halves the pair list (the world AABB of a rotated
     // box is loose) and all lanes test the same geom here.
+    // before that, the mesh's bounding sphere (sign only: no division, no root): for anything roundish
+    // it rejects what the box lets through
+    if (h) h = !mesh_bsphere_miss(p, pose + g, p.gstat + g, pnt, vec);
     if (h)
       h = prim_test(GEOM_BOX, pose + g, p.gstat + g, pnt[0], pnt[1], pnt[2], vec[0], vec[1],
                     vec[2]) >= 0;

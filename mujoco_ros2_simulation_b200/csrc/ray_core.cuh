@@ -783,6 +783,32 @@ B2_LEAF double mesh_trace(const MeshInfo* mesh, const MeshNode4* mnodes, const M
   return x;
 }
 
+// true if the ray certainly meets no triangle of mesh geom g: it misses the bounding sphere of the
+// mesh (MeshInfo::bs_*, inflated by 1e-6 -- nine orders of magnitude above the rounding of the fp64
+// triangle test, so even a hit that test would report through rounding lies inside it).  A cheaper
+// and, for roundish meshes, tighter filter than mj_rayMesh's own geom_size box; mj_rayMesh's result
+// for such a ray is -1 either way.
+B2_HD bool mesh_bsphere_miss(const CastParams& p, const GeomPose* gp, const GeomStatic* gsp,
+                             const double pnt[3], const double vec[3]) {
+#ifdef B2_NO_MESH_SPHERE
+  (void)p, (void)gp, (void)gsp, (void)pnt, (void)vec;
+  return false;
+#else
+  const MeshInfo* mi = p.mesh + gsp->dataid;
+#if B2_ON_DEVICE
+  const float4 b = __ldg(reinterpret_cast<const float4*>(mi->bs_c));
+  const double cx = b.x, cy = b.y, cz = b.z, r = b.w;
+#else
+  const double cx = mi->bs_c[0], cy = mi->bs_c[1], cz = mi->bs_c[2], r = mi->bs_r;
+#endif
+  const GeomPose P = ld_pose(gp);
+  const double cw[3] = {P.pos[0] + (P.mat[0] * cx + P.mat[1] * cy + P.mat[2] * cz),
+                        P.pos[1] + (P.mat[3] * cx + P.mat[4] * cy + P.mat[5] * cz),
+                        P.pos[2] + (P.mat[6] * cx + P.mat[7] * cy + P.mat[8] * cz)};
+  return sphere_miss(cw, r * r, pnt, vec);
+#endif
+}
+
 // One geom leaf some lane's ray may touch (warp-uniform g); h = this lane's slab test passed.
 // Primitives are tested here, all lanes on the same geom type.  Mesh geoms are handed to the warp
 // policy W: the device kernel appends a (ray, mesh geom) PAIR to a compacted global list that the
@@ -804,7 +830,7 @@ B2_HD void leaf_visit(const CastParams& p, const GeomPose* pose, int g, int type
 // in-place mesh handling (no pair list): used by policies that do not split
 B2_HD void mesh_inline(const CastParams& p, const GeomPose* pose, int g, bool h, Hit& hit,
                        const double pnt[3], const double vec[3], float tcap) {
-  if (h)
+  if (h && !mesh_bsphere_miss(p, pose + g, p.gstat + g, pnt, vec))
     hit_update(hit,
                mesh_trace(p.mesh, p.mnodes, p.mtris, pose + g, p.gstat + g, pnt[0], pnt[1], pnt[2],
                           vec[0], vec[1], vec[2], hit_tmax(hit, tcap)),

@@ -41,12 +41,17 @@ int fail(int code, const std::string& msg) {
       return fail(B2_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));        \
   } while (0)
 
+// bumped whenever a device / pinned buffer of the library is (re)allocated: captured CUDA graphs
+// bake buffer addresses in, so a graph is only replayed while this is what it was at capture
+std::atomic<unsigned long long> g_alloc_epoch{0};
+
 template <class T>
 struct DevBuf {
   T* ptr = nullptr;
   size_t cap = 0;  // elements
   cudaError_t reserve(size_t n) {
     if (n <= cap) return cudaSuccess;
+    g_alloc_epoch++;
     if (ptr) cudaFree(ptr);
     ptr = nullptr;
     cap = 0;
@@ -67,6 +72,7 @@ struct PinBuf {
   size_t cap = 0;
   cudaError_t reserve(size_t n) {
     if (n <= cap) return cudaSuccess;
+    g_alloc_epoch++;
     if (ptr) cudaFreeHost(ptr);
     ptr = nullptr;
     cap = 0;
@@ -179,6 +185,7 @@ struct LidarGraph {
   bool has_world = false;
   bool seen = false;  // the same shape ran once un-captured (all allocations exist)
   int kernels = 0;    // kernels inside the captured graph (b2_launch_count accounting)
+  unsigned long long alloc_epoch = 0;  // g_alloc_epoch when `seen` / captured
   cudaGraphExec_t exec = nullptr;
 };
 
@@ -1200,7 +1207,7 @@ int lidar_cast_begin(b2_lidar* l, int32_t nscan, const int32_t* scan_world, cons
                      (xyz ? 16 : 0);
     LidarGraph& g = l->graph;
     const bool same = g.nscan == nscan && g.mask == mask && g.topo_version == s->topo_version &&
-                      g.has_world == (scan_world != nullptr);
+                      g.has_world == (scan_world != nullptr) && g.alloc_epoch == g_alloc_epoch.load();
     const bool use_graph = env_int("B2_GRAPH", 1) != 0;
     if (use_graph && same && g.exec) {
       B2_CUDA(cudaGraphLaunch(g.exec, s->stream));
@@ -1243,6 +1250,7 @@ int lidar_cast_begin(b2_lidar* l, int32_t nscan, const int32_t* scan_world, cons
       g.seen = true;
       int rc = enqueue_small(l, hc, scan_world != nullptr, s->stream);
       if (rc != B2_OK) return rc;
+      g.alloc_epoch = g_alloc_epoch.load();  // after the plain run: every buffer it needs exists now
     }
     B2_CUDA(cudaEventRecord(l->cast_t1, s->stream));
     B2_CUDA(cudaEventRecord(l->all_done, s->stream));

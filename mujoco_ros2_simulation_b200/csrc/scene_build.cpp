@@ -69,6 +69,31 @@ bool build_mesh_bvhs(int nmesh, const int32_t* vertadr, const int32_t* vertnum,
     mi.node_base = (int32_t)out.nodes.size();
     mi.tri_base = (int32_t)out.tris.size();
     mi.ntri = nf;
+    {
+      // bounding sphere of the vertices the faces use: centre = middle of their box, radius = the
+      // farthest of them (double), inflated and rounded up
+      double lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+      for (int f = 0; f < nf; f++)
+        for (int c = 0; c < 3; c++)
+          for (int j = 0; j < 3; j++) {
+            const double v = vert[3 * face[3 * f + c] + j];
+            lo[j] = std::fmin(lo[j], v);
+            hi[j] = std::fmax(hi[j], v);
+          }
+      double r2 = 0.0;
+      for (int j = 0; j < 3; j++) mi.bs_c[j] = nf > 0 ? (float)(0.5 * (lo[j] + hi[j])) : 0.f;
+      for (int f = 0; f < nf; f++)
+        for (int c = 0; c < 3; c++) {
+          double d2 = 0.0;
+          for (int j = 0; j < 3; j++) {
+            const double d = (double)vert[3 * face[3 * f + c] + j] - (double)mi.bs_c[j];
+            d2 += d * d;
+          }
+          r2 = std::fmax(r2, d2);
+        }
+      const double r = std::sqrt(r2) * (1.0 + 1e-6) + 1e-30;
+      mi.bs_r = std::nextafter((float)r, INFINITY);
+    }
     if (nf == 0) {  // empty mesh: a root with four absent children
       MeshNode4 root{};
       for (int c = 0; c < 4; c++) {

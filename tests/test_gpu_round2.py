@@ -119,6 +119,27 @@ def test_begin_end_pinned_and_pageable_and_graph_replay(oracle, clutter, gpu_sce
     lid.close()
 
 
+def test_graph_survives_buffer_growth(oracle, clutter, gpu_scene):
+    """A captured single-scan graph bakes device addresses in.  A bigger cast in between reallocates
+    the lidar's and the scene's scratch: the next single scan must not replay the stale graph."""
+    cs = clutter
+    lid = engine.Lidar(gpu_scene, cs.lidar)
+    o = oracle.OracleScene(cs.model, cs.poses)
+    pos, mat = cs.sensor_poses(90, seed=41)
+    for i in range(4):                                   # plain, capture, replay, replay
+        lid.cast(pos[i:i + 1], mat[i:i + 1])
+    big = lid.cast(pos, mat)                             # 90 scans: every buffer grows
+    assert np.array_equal(big["geomid"][50], o.lidar_scan(cs.lidar, pos[50], mat[50], nthread=4)[1])
+    other = engine.Lidar(gpu_scene, scenes.LidarSpec(cs.lidar.local_dir[:4096], tile_w=0, bodyexclude=63))
+    other.cast(pos[:300 % 90 + 60], mat[:300 % 90 + 60])  # another sensor grows the scene's scratch too
+    for i in (5, 6, 7):
+        out = lid.cast(pos[i:i + 1], mat[i:i + 1], want=("ranges", "geomid"))
+        r, g, _ = o.lidar_scan(cs.lidar, pos[i], mat[i], nthread=4)
+        assert np.array_equal(out["ranges"][0], r) and np.array_equal(out["geomid"][0], g)
+    other.close()
+    lid.close()
+
+
 def test_latest_wins_pose_mirror(oracle, clutter):
     """After the first update, host updates of all worlds only fill a pinned slot; the next cast
     uploads the NEWEST one.  Interleaved with partial / device updates the order is kept."""
