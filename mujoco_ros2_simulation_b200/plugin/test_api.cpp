@@ -381,6 +381,36 @@ int b2p_refresh_stress(void* hp, int n_el, int n_az, double hz, double seconds, 
   return 0;
 }
 
+// what the wrappers logged so far (stand-in rclcpp logger), newline separated; returns the line count
+int b2p_logs(void* hp, char* out, int cap)
+{
+  auto* h = static_cast<Harness*>(hp);
+  const auto& lines = *h->node->get_logger().lines;
+  std::string all;
+  for (const auto& l : lines)
+  {
+    all += l;
+    all += '\n';
+  }
+  if (out != nullptr && cap > 0)
+  {
+    std::strncpy(out, all.c_str(), (size_t)cap - 1);
+    out[cap - 1] = 0;
+  }
+  return (int)lines.size();
+}
+
+// publish counts of camera k: image, depth, camera_info, points
+int b2p_camera_pub_counts(void* hp, int k, int* out4)
+{
+  auto& c = static_cast<Harness*>(hp)->cameras->cameras().at(k);
+  out4[0] = (int)c.image_pub->count();
+  out4[1] = (int)c.depth_image_pub->count();
+  out4[2] = (int)c.camera_info_pub->count();
+  out4[3] = (int)c.cloud_pub->count();
+  return 0;
+}
+
 void b2p_destroy(void* hp)
 {
   auto* h = static_cast<Harness*>(hp);

@@ -76,6 +76,10 @@ def lib():
         L.b2p_camera_set_gl_depth.argtypes = [C.c_void_p, C.c_void_p]
         L.b2p_camera_rgb.restype = C.c_int
         L.b2p_camera_rgb.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+        L.b2p_logs.restype = C.c_int
+        L.b2p_logs.argtypes = [C.c_void_p, C.c_char_p, C.c_int]
+        L.b2p_camera_pub_counts.restype = C.c_int
+        L.b2p_camera_pub_counts.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
         L.b2p_refresh_stress.restype = C.c_int
         L.b2p_refresh_stress.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_double, C.c_void_p]
         L.b2p_sizeof_mjmodel.restype = C.c_size_t
@@ -192,6 +196,16 @@ class PluginHarness:
 
     def run_threads(self, ms: int) -> int:
         return self.L.b2p_run_threads(self.h, ms)
+
+    def logs(self) -> list:
+        buf = C.create_string_buffer(1 << 16)
+        self.L.b2p_logs(self.h, buf, len(buf))
+        return [l for l in buf.value.decode().split("\n") if l]
+
+    def camera_pub_counts(self, k=0) -> dict:
+        out = np.zeros(4, np.int32)
+        self.L.b2p_camera_pub_counts(self.h, k, out.ctypes.data)
+        return dict(zip(("image", "depth", "info", "points"), (int(v) for v in out)))
 
     def refresh_stress(self, n_el=64, n_az=2048, hz=1500.0, seconds=2.0) -> dict:
         """physics-thread refresh at `hz` while a sensor thread casts back to back (test_api.cpp)"""

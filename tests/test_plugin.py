@@ -92,6 +92,34 @@ def test_register_cameras_message_layout(plug, scene):
     h.close()
 
 
+def test_registration_is_logged_and_strict(plug, scene):
+    """The reference logs what it registers and warns about what it skips (ref:src/mujoco_lidar.cpp
+    :140-150,178-185); so does the drop-in.  New: replicas beyond the URDF's ray count are reported,
+    and rangefinders of one lidar with different cutoffs are refused (MuJoCo applies sensor_cutoff
+    per sensor, the cast takes one per lidar)."""
+    h = plug.PluginHarness(scene, INFO)
+    assert h.register() == 0, h.error()
+    logs = h.logs()
+    assert any(l.startswith("INFO: lidar 'lidar'") and "24 rays" in l for l in logs)
+    assert any(l.startswith("INFO: camera 'camera'") for l in logs)
+    h.close()
+    # the URDF describes fewer rays than the MJCF replicates: the surplus is dropped with a warning
+    short = INFO.replace("max_angle=0.3", "max_angle=0.2")          # int(0.5 / 0.025) + 1 = 21 rays
+    h = plug.PluginHarness(scene, short)
+    assert h.register() == 0, h.error()
+    assert h.lidar_info()["num_rangefinders"] == 21
+    assert sum("lies beyond the 21 rays" in l for l in h.logs()) == 3
+    h.close()
+    # differing cutoffs inside one lidar
+    import copy
+    sc2 = copy.deepcopy(scene)
+    sc2.rangefinders[5].cutoff = 3.0
+    h = plug.PluginHarness(sc2, INFO)
+    assert h.register() == -1 and "different cutoffs" in h.error()
+    assert any(l.startswith("ERROR:") and "different cutoffs" in l for l in h.logs())
+    h.close()
+
+
 def test_no_cpu_fallback_in_plugin(plug, scene, has_gpu):
     if has_gpu:
         pytest.skip("a GPU is present")
@@ -149,6 +177,8 @@ def test_camera_publish_cycle(plug, scene, oracle):
     assert 0.0 <= gl.min() and gl.max() <= 1.0 and (gl < 1.0).mean() > 0.3   # arm + floor in view
     assert np.array_equal(depth, oracle.depth_linearise_flip(gl[None], scene.znear, scene.zfar, 1.0)[0])
     assert np.isfinite(cloud[..., 2]).all() and np.array_equal(cloud[..., 2], depth)
+    # ray casting renders depth only: no colour image goes out, everything else does
+    assert h.camera_pub_counts() == {"image": 0, "depth": 1, "info": 1, "points": 1}
     h.close()
 
 
