@@ -14,6 +14,7 @@
 #include <thread>
 #include <vector>
 
+#include "cdr.hpp"
 #include "mujoco_cameras.hpp"
 #include "mujoco_lidar.hpp"
 
@@ -398,6 +399,32 @@ int b2p_logs(void* hp, char* out, int cap)
     out[cap - 1] = 0;
   }
   return (int)lines.size();
+}
+
+// the last published message of a publisher as it would go on the wire (classic CDR, little endian):
+// which = 0 LaserScan of lidar k, 1 depth Image, 2 CameraInfo, 3 PointCloud2, 4 colour Image of camera k.
+// Returns the byte count (call with out = nullptr to size the buffer).
+long b2p_wire_bytes(void* hp, int which, int k, uint8_t* out, long cap)
+{
+  auto* h = static_cast<Harness*>(hp);
+  std::vector<uint8_t> bytes;
+  if (which == 0)
+  {
+    bytes = b2cdr::serialize(h->lidar->lidars().at(k).scan_pub->last());
+  }
+  else
+  {
+    auto& c = h->cameras->cameras().at(k);
+    bytes = which == 1 ? b2cdr::serialize(c.depth_image_pub->last()) :
+            which == 2 ? b2cdr::serialize(c.camera_info_pub->last()) :
+            which == 3 ? b2cdr::serialize(c.cloud_pub->last()) :
+                         b2cdr::serialize(c.image_pub->last());
+  }
+  if (out != nullptr && cap >= (long)bytes.size())
+  {
+    std::memcpy(out, bytes.data(), bytes.size());
+  }
+  return (long)bytes.size();
 }
 
 // publish counts of camera k: image, depth, camera_info, points

@@ -76,6 +76,8 @@ def lib():
         L.b2p_camera_set_gl_depth.argtypes = [C.c_void_p, C.c_void_p]
         L.b2p_camera_rgb.restype = C.c_int
         L.b2p_camera_rgb.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+        L.b2p_wire_bytes.restype = C.c_long
+        L.b2p_wire_bytes.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_long]
         L.b2p_logs.restype = C.c_int
         L.b2p_logs.argtypes = [C.c_void_p, C.c_char_p, C.c_int]
         L.b2p_camera_pub_counts.restype = C.c_int
@@ -196,6 +198,14 @@ class PluginHarness:
 
     def run_threads(self, ms: int) -> int:
         return self.L.b2p_run_threads(self.h, ms)
+
+    def wire_bytes(self, which: str, k=0) -> bytes:
+        """last published message as classic CDR (plugin/cdr.hpp): 'scan', 'depth', 'info', 'points', 'image'"""
+        code = {"scan": 0, "depth": 1, "info": 2, "points": 3, "image": 4}[which]
+        n = self.L.b2p_wire_bytes(self.h, code, k, None, 0)
+        buf = (C.c_uint8 * n)()
+        self.L.b2p_wire_bytes(self.h, code, k, buf, n)
+        return bytes(buf)
 
     def logs(self) -> list:
         buf = C.create_string_buffer(1 << 16)
