@@ -143,6 +143,8 @@ struct b2_scene {
   } pm;
   int topo_version = 0;  // bumped by every topology (re)build: invalidates captured graphs
   std::atomic<int> dependents{0};  // live lidars / cameras bound to this scene
+  bool capturing = false;  // the scene's stream is being captured into a graph (scene mutex held)
+  cudaEvent_t sync_mark[2] = {nullptr, nullptr};  // b2_scene_sync
   cudaEvent_t copy_fork = nullptr, copy_join = nullptr;  // b2_scene_copy_async / b2_scene_join
   cudaEvent_t copy_fence[2] = {nullptr, nullptr};        // b2_scene_copy_fence (one-step lag)
   bool copy_fence_used[2] = {false, false};
@@ -665,6 +667,8 @@ int b2_scene_destroy(b2_scene* s) {
     if (s->stage_done[i]) cudaEventDestroy(s->stage_done[i]);
     if (s->refit_done[i]) cudaEventDestroy(s->refit_done[i]);
   }
+  for (int i = 0; i < 2; i++)
+    if (s->sync_mark[i]) cudaEventDestroy(s->sync_mark[i]);
   if (s->copy_fork) cudaEventDestroy(s->copy_fork);
   if (s->copy_join) cudaEventDestroy(s->copy_join);
   for (int i = 0; i < 2; i++)
@@ -682,6 +686,10 @@ int b2_scene_destroy(b2_scene* s) {
 // consumer with the scene mutex held.  H2D rides the copy stream; the refit waits for it on the
 // scene's stream; the upload into a d_raw half waits for the refit that last read that half.
 static int flush_pending(b2_scene* s) {
+  // never inside a stream capture: an upload + refit baked into a replayed graph would re-install
+  // stale poses on every replay.  The caller flushed before it began capturing; whatever the
+  // producer left since then is picked up by the next consumer.
+  if (s->capturing) return B2_OK;
   b2_scene::PoseMirror& pm = s->pm;
   {
     std::lock_guard<std::mutex> g(pm.idx);
@@ -877,12 +885,18 @@ int b2_scene_sync(b2_scene* s) {
   if (!s) return fail(B2_ERR_INVALID, "null scene");
   B2_CUDA(cudaSetDevice(s->device));
   {
+    // markers are recorded under the scene mutex and waited for outside it: another thread may be
+    // capturing the scene's stream meanwhile, and a stream-wide synchronize would break its capture
     std::lock_guard<std::recursive_mutex> lock(s->mtx);
     int rc = flush_pending(s);
     if (rc != B2_OK) return rc;
+    for (int i = 0; i < 2; i++)
+      if (!s->sync_mark[i]) B2_CUDA(cudaEventCreateWithFlags(&s->sync_mark[i], cudaEventDisableTiming));
+    B2_CUDA(cudaEventRecord(s->sync_mark[0], s->stream));
+    B2_CUDA(cudaEventRecord(s->sync_mark[1], s->copy_stream));
   }
-  B2_CUDA(cudaStreamSynchronize(s->stream));
-  B2_CUDA(cudaStreamSynchronize(s->copy_stream));
+  B2_CUDA(cudaEventSynchronize(s->sync_mark[0]));
+  B2_CUDA(cudaEventSynchronize(s->sync_mark[1]));
   return B2_OK;
 }
 
@@ -1004,8 +1018,11 @@ int b2_lidar_create(b2_scene* s, const b2_lidar_desc* d, b2_lidar** out) {
 int b2_lidar_destroy(b2_lidar* l) {
   if (!l) return B2_OK;
   cudaSetDevice(l->scene->device);
-  cudaStreamSynchronize(l->scene->stream);
-  cudaStreamSynchronize(l->scene->copy_stream);
+  {
+    std::lock_guard<std::recursive_mutex> lock(l->scene->mtx);  // nobody is capturing the stream
+    cudaStreamSynchronize(l->scene->stream);
+    cudaStreamSynchronize(l->scene->copy_stream);
+  }
   l->d_local_dir.release();
   l->d_elim.release();
   l->d_spos.release();
@@ -1216,7 +1233,9 @@ int lidar_cast_begin(b2_lidar* l, int32_t nscan, const int32_t* scan_world, cons
       cudaGraph_t graph = nullptr;
       const long long l0 = g_launches.load();
       B2_CUDA(cudaStreamBeginCapture(s->stream, cudaStreamCaptureModeThreadLocal));
+      s->capturing = true;
       int rc = enqueue_small(l, hc, scan_world != nullptr, s->stream);
+      s->capturing = false;
       cudaError_t e = cudaStreamEndCapture(s->stream, &graph);
       g.kernels = (int)(g_launches.load() - l0);  // counted once here = the first replay
       if (rc != B2_OK || e != cudaSuccess || !graph) {
@@ -1526,7 +1545,11 @@ int b2_camera_create(b2_scene* scene, int32_t device, const b2_camera_desc* d, b
 int b2_camera_destroy(b2_camera* c) {
   if (!c) return B2_OK;
   cudaSetDevice(c->device);
-  if (c->stream) cudaStreamSynchronize(c->stream);
+  {
+    std::unique_lock<std::recursive_mutex> lock;
+    if (c->scene) lock = std::unique_lock<std::recursive_mutex>(c->scene->mtx);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+  }
   c->d_in.release();
   c->d_depth.release();
   c->d_cloud.release();
@@ -1597,21 +1620,29 @@ int b2_depth_to_cloud(b2_camera* c, int32_t ncam, const float* gl_depth, float* 
   B2_CUDA(cudaSetDevice(c->device));
   const size_t npix = (size_t)ncam * c->desc.width * c->desc.height;
   const size_t pf = (size_t)c->desc.point_step / 4;
-  B2_CUDA(c->d_in.reserve(npix));
-  if (depth32fc1) B2_CUDA(c->d_depth.reserve(npix));
-  if (cloud) B2_CUDA(c->d_cloud.reserve(npix * pf));
-  B2_CUDA(cudaMemcpyAsync(c->d_in.ptr, gl_depth, npix * sizeof(float), cudaMemcpyHostToDevice,
-                          c->stream));
-  int rc = b2_depth_to_cloud_device(c, ncam, c->d_in.ptr, depth32fc1 ? c->d_depth.ptr : nullptr,
-                                    cloud ? c->d_cloud.ptr : nullptr);
-  if (rc != B2_OK) return rc;
-  if (depth32fc1)
-    B2_CUDA(cudaMemcpyAsync(depth32fc1, c->d_depth.ptr, npix * sizeof(float),
-                            cudaMemcpyDeviceToHost, c->stream));
-  if (cloud)
-    B2_CUDA(cudaMemcpyAsync(cloud, c->d_cloud.ptr, npix * pf * sizeof(float),
-                            cudaMemcpyDeviceToHost, c->stream));
-  B2_CUDA(cudaStreamSynchronize(c->stream));
+  if (!c->done) B2_CUDA(cudaEventCreateWithFlags(&c->done, cudaEventDisableTiming));
+  {
+    // a camera bound to a scene shares the scene's stream: enqueue everything under the scene mutex,
+    // wait on an event outside it (no stream-wide synchronize: see b2_scene_sync)
+    std::unique_lock<std::recursive_mutex> lock;
+    if (c->scene) lock = std::unique_lock<std::recursive_mutex>(c->scene->mtx);
+    B2_CUDA(c->d_in.reserve(npix));
+    if (depth32fc1) B2_CUDA(c->d_depth.reserve(npix));
+    if (cloud) B2_CUDA(c->d_cloud.reserve(npix * pf));
+    B2_CUDA(cudaMemcpyAsync(c->d_in.ptr, gl_depth, npix * sizeof(float), cudaMemcpyHostToDevice,
+                            c->stream));
+    int rc = b2_depth_to_cloud_device(c, ncam, c->d_in.ptr, depth32fc1 ? c->d_depth.ptr : nullptr,
+                                      cloud ? c->d_cloud.ptr : nullptr);
+    if (rc != B2_OK) return rc;
+    if (depth32fc1)
+      B2_CUDA(cudaMemcpyAsync(depth32fc1, c->d_depth.ptr, npix * sizeof(float),
+                              cudaMemcpyDeviceToHost, c->stream));
+    if (cloud)
+      B2_CUDA(cudaMemcpyAsync(cloud, c->d_cloud.ptr, npix * pf * sizeof(float),
+                              cudaMemcpyDeviceToHost, c->stream));
+    B2_CUDA(cudaEventRecord(c->done, c->stream));
+  }
+  B2_CUDA(cudaEventSynchronize(c->done));
   return B2_OK;
 }
 

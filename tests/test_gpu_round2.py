@@ -278,3 +278,62 @@ def test_refresh_cost_while_the_gpu_is_busy():
     assert res["refreshes"] > 2500 and res["casts"] > 100
     assert res["p99_us"] < 100.0, res
     h.close()
+
+
+def test_three_threads_like_the_plugin(oracle, clutter):
+    """physics thread refreshing, lidar thread casting single scans (graph capture + replay), camera
+    thread rendering through the blocking call and syncing -- all on one scene, as in the plugin
+    (ref:src/mujoco_system_interface.cpp threads :595,:724, lidar.cpp:216, cameras.cpp:141).  No
+    call may fail (a stream-wide synchronize during another thread's capture would), and the
+    results are the oracle's."""
+    import threading
+    cs = clutter
+    s = engine.Scene(cs.model, nworld=1)
+    s.update_poses(cs.poses)
+    lid = engine.Lidar(s, cs.lidar)
+    cam = engine.DepthCamera(scenes.CameraSpec(64, 48, 58.0), scene=s)
+    pos, mat = cs.sensor_poses(8, seed=61)
+    R = np.array([[0, 0, -1.0], [-1.0, 0, 0], [0, 1.0, 0]]).reshape(1, 9)
+    cp = np.array([[3.0, 0.0, 1.5]])
+    errors, scans, frames = [], {}, []
+    stop = threading.Event()
+
+    def physics():
+        try:
+            while not stop.is_set():
+                s.update_poses(cs.poses)
+        except Exception as e:  # noqa: BLE001
+            errors.append(("physics", repr(e)))
+
+    def lidar_thread():
+        try:
+            for it in range(120):
+                i = it % 8
+                scans[i] = lid.cast(pos[i:i + 1], mat[i:i + 1], want=("ranges", "geomid"))
+        except Exception as e:  # noqa: BLE001
+            errors.append(("lidar", repr(e)))
+
+    def camera_thread():
+        try:
+            for _ in range(40):
+                frames.append(cam.render_to_cloud(cp, R, want=("depth",))[1])
+                s.sync()
+        except Exception as e:  # noqa: BLE001
+            errors.append(("camera", repr(e)))
+
+    ts = [threading.Thread(target=f) for f in (physics, lidar_thread, camera_thread)]
+    for t in ts:
+        t.start()
+    ts[1].join()
+    ts[2].join()
+    stop.set()
+    ts[0].join()
+    assert not errors, errors
+    o = oracle.OracleScene(cs.model, cs.poses)
+    for i in range(8):
+        r, g, _ = o.lidar_scan(cs.lidar, pos[i], mat[i], nthread=4)
+        assert np.array_equal(scans[i]["ranges"][0], r) and np.array_equal(scans[i]["geomid"][0], g)
+    assert len(frames) == 40 and all(np.array_equal(f, frames[0]) for f in frames)
+    cam.close()
+    lid.close()
+    s.close()
