@@ -1296,22 +1296,34 @@ int lidar_cast_begin(b2_lidar* l, int32_t nscan, const int32_t* scan_world, cons
                            (dist ? 8.0 : 0.0) + (xyz ? 12.0 : 0.0);
   const double copy_ns_per_ray = out_bytes / 50.0;
   const double cast_ns_per_ray = l->cast_ns_per_ray > 0 ? l->cast_ns_per_ray : 0.12;
-  int nchunk = env_int("B2_E2E_CHUNKS", copy_ns_per_ray > cast_ns_per_ray ? 16 : 4);
+  const bool copy_bound = copy_ns_per_ray > cast_ns_per_ray;
+  int nchunk = env_int("B2_E2E_CHUNKS", copy_bound ? 16 : 0);
   if (nchunk > nscan) nchunk = nscan;
-  if (nchunk < 1) nchunk = 1;
-  // equal pieces, except that the first and the last one are cut into quarters: nothing overlaps
-  // the cast of the first piece nor the copy of the last one
   std::vector<int>& bounds = hc.bounds;
-  for (int c = 0; c < nchunk; c++) {
-    const int b0 = (int)((long long)nscan * c / nchunk), b1 = (int)((long long)nscan * (c + 1) / nchunk);
-    if (bounds.empty() || b0 > bounds.back()) bounds.push_back(b0);
-    if (nchunk > 1 && (c == 0 || c == nchunk - 1)) {
-      for (int q = 1; q < 4; q++) {
-        const int b = b0 + (int)((long long)(b1 - b0) * q / 4);
-        if (b > bounds.back() && b < nscan) bounds.push_back(b);
+  if (nchunk >= 1) {
+    // read-back bound: equal pieces, except that the first and the last one are cut into quarters:
+    // nothing overlaps the cast of the first piece nor the copy of the last one
+    for (int c = 0; c < nchunk; c++) {
+      const int b0 = (int)((long long)nscan * c / nchunk), b1 = (int)((long long)nscan * (c + 1) / nchunk);
+      if (bounds.empty() || b0 > bounds.back()) bounds.push_back(b0);
+      if (nchunk > 1 && (c == 0 || c == nchunk - 1)) {
+        for (int q = 1; q < 4; q++) {
+          const int b = b0 + (int)((long long)(b1 - b0) * q / 4);
+          if (b > bounds.back() && b < nscan) bounds.push_back(b);
+        }
       }
     }
+  } else {
+    // cast bound: every extra piece costs the launch tails of its kernels (~0.2 ms), and only the
+    // LAST piece's read-back is exposed: three quarters, then halving pieces -- the first copy starts
+    // after a quarter of the cast, the exposed one is a sixteenth of the data
+    static const int kNum[] = {0, 4, 8, 12, 14, 15};
+    for (int k = 0; k < 6; k++) {
+      const int b = (int)((long long)nscan * kNum[k] / 16);
+      if (bounds.empty() || b > bounds.back()) bounds.push_back(b);
+    }
   }
+  if (bounds.empty()) bounds.push_back(0);
   bounds.push_back(nscan);
   while (l->piece_done.size() + 1 < bounds.size()) {
     cudaEvent_t ev = nullptr;
