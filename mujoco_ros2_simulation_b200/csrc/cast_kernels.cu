@@ -568,6 +568,32 @@ __global__ void __launch_bounds__(kCastThreads, B2_CAST_MINBLOCKS)
 #ifndef B2_MESH_REFILL
 #define B2_MESH_REFILL 16  // idle lanes per warp that trigger a refill (2..16 measured: 16 best)
 #endif
+#ifndef B2_MESH_SMEM_STACK
+// stack entries per lane kept in shared memory (deeper ones in local memory).  0 = all in local memory:
+// 12 measured 10.25 Grays/s against 10.34 for 0 -- the stack was never what the L1 misses were about
+#define B2_MESH_SMEM_STACK 0
+#endif
+#ifndef B2_MESH_PREFETCH
+// prefetch.global.L1 of (bit 0) a leaf's triangles when the descent reaches it, (bit 1) the runner-up
+// child.  Off: 0 / 1 / 2 / 3 measured 10.25 / 10.01 / 10.08 / 9.89 Grays/s -- the kernel waits on the
+// node it needs NOW; hints for later nodes only add instructions and evict lines
+#define B2_MESH_PREFETCH 0
+#endif
+#ifdef B2_MESH_STATS
+// debug build only: per-pair work of the mesh kernel (tools/mesh_stats.py)
+__device__ unsigned long long g_mesh_stats[64];
+extern "C" int b2_debug_mesh_stats(unsigned long long* out, int reset) {
+  if (out) cudaMemcpyFromSymbol(out, g_mesh_stats, sizeof(g_mesh_stats));
+  if (reset) {
+    unsigned long long z[64] = {0};
+    cudaMemcpyToSymbol(g_mesh_stats, z, sizeof(z));
+  }
+  return 0;
+}
+#endif
+__device__ __forceinline__ void mesh_prefetch(const void* ptr) {
+  asm volatile("prefetch.global.L1 [%0];" ::"l"(ptr));
+}
 template <int MODE>
 __global__ void __launch_bounds__(kMeshThreads, B2_MESH_MINBLOCKS)
     mesh_pairs_kernel(const __grid_constant__ CastParams p) {
@@ -576,7 +602,9 @@ __global__ void __launch_bounds__(kMeshThreads, B2_MESH_MINBLOCKS)
   const int lane = threadIdx.x & 31;
   const unsigned lt = (1u << lane) - 1u;
   constexpr int32_t kDone = kEmptyChild;
-
+  // (Spreading a small launch's pairs over all resident warps -- 3 lanes per warp instead of 32 for
+  // the ~11 k pairs of one scan -- did not shorten it: 94 vs 114 us under ncu, 160 us per scan either
+  // way in graph replay.  A pair is a ~1400-instruction dependent chain; profiles/r02_sweeps.txt r02y.)
   bool have = false;
   int pair = 0, slot = 0;
   double lpnt[3], lvec[3], b0[3], b1[3], x = -1;
@@ -585,18 +613,40 @@ __global__ void __launch_bounds__(kMeshThreads, B2_MESH_MINBLOCKS)
   const MeshNode4* nodes = nullptr;
   const MeshTri* tris = nullptr;
   int32_t cur = kDone;
-  int32_t stack[kMeshStack];
-  float stack_t[kMeshStack];
+  // traversal stack of (link, entry distance): the first entries of every lane in shared memory
+  // ([depth][thread]: conflict-free), the rest -- deep trees only -- in local memory
+  __shared__ uint2 s_stack[B2_MESH_SMEM_STACK > 0 ? B2_MESH_SMEM_STACK : 1][kMeshThreads];
+  uint2 l_stack[kMeshStack - B2_MESH_SMEM_STACK];
   int sp = 0;
+#ifdef B2_MESH_STATS
+  unsigned st_nodes = 0, st_tris = 0;
+  long long st_t0 = 0;
+#endif
+  auto push = [&](int32_t link, float t) {
+    const uint2 e = make_uint2((uint32_t)link, __float_as_uint(t));
+    if (sp < B2_MESH_SMEM_STACK) s_stack[sp][threadIdx.x] = e;
+    else l_stack[sp - B2_MESH_SMEM_STACK] = e;
+    sp++;
+  };
+  // next stacked node that can still beat tmax, or kDone
+  auto pop = [&]() -> int32_t {
+    while (sp > 0) {
+      --sp;
+      const uint2 e = sp < B2_MESH_SMEM_STACK ? s_stack[sp][threadIdx.x] : l_stack[sp - B2_MESH_SMEM_STACK];
+      if (__uint_as_float(e.y) <= tmax) return (int32_t)e.x;
+    }
+    return kDone;
+  };
 
   for (;;) {
-    // (1) refill: idle lanes take the next pairs; wait until a quarter of the warp is idle so the
+    // (1) refill: idle lanes take the next pairs; wait until half of the warp is idle so the
     //     per-pair setup (ray_map, basis, reciprocals) does not run for one lane at a time
     const unsigned idle = __ballot_sync(0xffffffffu, !have);
-    if (idle == 0xffffffffu || __popc(idle) >= B2_MESH_REFILL) {
+    const int missing = __popc(idle);
+    if (idle == 0xffffffffu || missing >= B2_MESH_REFILL) {
       const int leader = __ffs(idle) - 1;
       int base = 0;
-      if (lane == leader) base = atomicAdd(p.ms.counters + 3, __popc(idle));
+      if (lane == leader) base = atomicAdd(p.ms.counters + 3, missing);
       base = __shfl_sync(0xffffffffu, base, leader);
       if (!have) {
         pair = base + __popc(idle & lt);
@@ -624,6 +674,10 @@ __global__ void __launch_bounds__(kMeshThreads, B2_MESH_MINBLOCKS)
           sp = 0;
           cur = 0;
           have = true;
+#ifdef B2_MESH_STATS
+          st_nodes = st_tris = 0;
+          st_t0 = clock64();
+#endif
         }
       }
     }
@@ -634,6 +688,9 @@ __global__ void __launch_bounds__(kMeshThreads, B2_MESH_MINBLOCKS)
     // (cap 2 / 3 / 4 / 6 / none measured 9.39 / 9.61 / 9.61 / 9.71 / 9.62 Grays/s)
     for (int it = 0; it < B2_MESH_INNER_CAP && have && cur >= 0; it++) {
       const MeshNode4 n = ld_node4(nodes + cur);
+#ifdef B2_MESH_STATS
+      st_nodes++;
+#endif
       float t[4];
       int32_t lk[4];
 #pragma unroll
@@ -663,22 +720,22 @@ __global__ void __launch_bounds__(kMeshThreads, B2_MESH_MINBLOCKS)
         // enter the nearest; the others wait on the stack, farthest first
 #pragma unroll
         for (int c = 3; c >= 1; c--) {
-          if (t[c] < INFINITY && sp < kMeshStack) {
-            stack[sp] = lk[c];
-            stack_t[sp] = t[c];
-            sp++;
-          }
+          if (t[c] < INFINITY && sp < kMeshStack) push(lk[c], t[c]);
         }
         cur = lk[0];
-      } else {
-        cur = kDone;
-        while (sp > 0) {
-          --sp;
-          if (stack_t[sp] <= tmax) {
-            cur = stack[sp];
-            break;
-          }
+        if ((B2_MESH_PREFETCH & 2) && t[1] < INFINITY) {
+          // the runner-up is the most likely next stop after the nearest subtree
+          if (lk[1] >= 0) mesh_prefetch(nodes + lk[1]);
+          else mesh_prefetch(tris + (~lk[1] >> 2));
         }
+      } else {
+        cur = pop();
+      }
+      if ((B2_MESH_PREFETCH & 1) && cur < 0 && cur != kDone) {
+        // the leaf is served in phase (3), after the other lanes' descents: fetch its triangles now
+        const MeshTri* t0 = tris + (~cur >> 2);
+        mesh_prefetch(t0);
+        if ((~cur & 3) >= 2) mesh_prefetch(t0 + 2);
       }
     }
 
@@ -690,23 +747,35 @@ __global__ void __launch_bounds__(kMeshThreads, B2_MESH_MINBLOCKS)
       for (int i = 0; i < cnt; i++) {
         const MeshTri tr = ld_tri(tris + first + i);
         const double sol = ray_triangle(tr.v0, tr.v1, tr.v2, lpnt, lvec, b0, b1);
+#ifdef B2_MESH_STATS
+        st_tris++;
+#endif
         if (sol >= 0 && (x < 0 || sol < x)) {
           x = sol;
           tmax = fminf(tmax, f32_up(sol));
         }
       }
-      cur = kDone;
-      while (sp > 0) {
-        --sp;
-        if (stack_t[sp] <= tmax) {
-          cur = stack[sp];
-          break;
-        }
-      }
+      cur = pop();
     }
 
     // (4) pair finished: publish
     if (have && cur == kDone) {
+#ifdef B2_MESH_STATS
+      {
+        const unsigned long long cyc = (unsigned long long)(clock64() - st_t0);
+        atomicAdd(g_mesh_stats + 0, 1ull);
+        atomicAdd(g_mesh_stats + 1, (unsigned long long)st_nodes);
+        atomicAdd(g_mesh_stats + 2, (unsigned long long)st_tris);
+        atomicAdd(g_mesh_stats + 3, cyc);
+        atomicMax(g_mesh_stats + 4, (unsigned long long)st_nodes);
+        atomicMax(g_mesh_stats + 5, (unsigned long long)st_tris);
+        atomicMax(g_mesh_stats + 6, cyc);
+        atomicAdd(g_mesh_stats + 7, x >= 0 ? 1ull : 0ull);
+        atomicAdd(g_mesh_stats + 16 + ::min(15, 32 - __clz(st_nodes)), 1ull);          // log2 histogram of nodes
+        atomicAdd(g_mesh_stats + 32 + ::min(15, 32 - __clz(st_tris)), 1ull);           // ... of triangles
+        atomicAdd(g_mesh_stats + 48 + ::min(15, ::max(0, 64 - __clzll(cyc) - 8)), 1ull);  // ... of cycles / 256
+      }
+#endif
       p.ms.pair_x[pair] = x;
       if (x >= 0) atomicMin(p.ms.aff_bits + slot, (unsigned long long)__double_as_longlong(x));
       have = false;
