@@ -1709,6 +1709,9 @@ int b2_rgb_flip_device(b2_camera* c, int32_t ncam, const uint8_t* d_rgb_gl, uint
   if (ncam == 0) return B2_OK;
   if (!d_rgb_gl || !d_rgb_out) return fail(B2_ERR_INVALID, "null image buffer");
   B2_CUDA(cudaSetDevice(c->device));
+  // shares the scene's stream: never enqueue while another thread captures it into a graph
+  std::unique_lock<std::recursive_mutex> lock;
+  if (c->scene) lock = std::unique_lock<std::recursive_mutex>(c->scene->mtx);
   B2_CUDA(launch_rgb_flip(d_rgb_gl, d_rgb_out, ncam, c->desc.width, c->desc.height, c->stream));
   g_launches++;
   return B2_OK;
