@@ -783,6 +783,190 @@ __global__ void __launch_bounds__(kMeshThreads, B2_MESH_MINBLOCKS)
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// K2b for SMALL launches (one scan: ~10 k pairs): G lanes per pair
+// ---------------------------------------------------------------------------------------------
+//
+// One lane per pair makes a small launch as long as its heaviest pair: a ray that grazes a mesh walks
+// ~60 nodes and ~30 triangles, an ~11 000-instruction dependent chain (~95 us), while the machine
+// idles (tools/mesh_stats.py).  Here a GROUP of G lanes (8, 16 or 32: the fewer pairs, the wider)
+// shares one pair and one traversal stack in shared memory.  Per round, quad q of the group pops
+// entry q from the top of the stack; its four lanes test the four children of that node -- or up to
+// four triangles of that leaf -- at once; hits are pushed back with ballot / popc addressing, the
+// nearest child of the nearest node on top.  The walk is no longer strictly nearest-first, which
+// costs a few extra nodes and is why the one-lane kernel stays the throughput path; the result
+// cannot differ: it is the exact minimum over the fp64 triangle tests, and boxes only ever cull what
+// lies beyond a hit already found.
+constexpr int kCoopStackPerWarp = 512;  // stack entries per warp, split between its 32 / G groups
+constexpr int kCoopReserve = 64;        // >= 3 * depth + 1 of any mesh tree (scene_build.cpp)
+template <int MODE, int G>
+__device__ __forceinline__ void mesh_pairs_coop(const CastParams& p, int npair, uint2* warp_stk) {
+  const float tcap = (MODE == MODE_MULTIRAY) ? f32_up(p.cutoff) : FLT_MAX;
+  const int lane = threadIdx.x & 31;
+  const int gl = lane & (G - 1);   // lane within the group
+  const int g0 = lane & ~(G - 1);  // first lane of the group
+  const int q0 = lane & ~3;        // first lane of the quad
+  const int quad = gl >> 2, child = lane & 3;
+  constexpr int nq = G >> 2, ngroup = 32 / G;
+  constexpr int cap = kCoopStackPerWarp / ngroup, cap_soft = cap - kCoopReserve;
+  constexpr unsigned leaders = G == 32 ? 1u : (G == 16 ? 0x00010001u : 0x01010101u);
+  const unsigned gmask = G == 32 ? 0xffffffffu : (((1u << G) - 1u) << g0);
+  uint2* stk = warp_stk + (g0 / G) * cap;
+
+  bool have = false;
+  int pair = 0, slot = 0, sp = 0;
+  double lpnt[3], lvec[3], b0[3], b1[3], x = -1;
+  RayF rf;
+  float tmax = 0.f;
+  const MeshNode4* nodes = nullptr;
+  const MeshTri* tris = nullptr;
+
+  for (;;) {
+    // (1) refill: groups without a pair take the next ones (every lane of a group sets the pair up
+    //     for itself: same loads, same arithmetic, same values)
+    const unsigned idle = __ballot_sync(0xffffffffu, !have) & leaders;
+    if (idle == leaders || __popc(idle) * 2 >= ngroup) {
+      const int first = __ffs(idle) - 1;
+      int base = 0;
+      if (lane == first) base = atomicAdd(p.ms.counters + 3, __popc(idle));
+      base = __shfl_sync(0xffffffffu, base, first);
+      const bool fresh = !have;
+      if (fresh) {
+        pair = base + __popc(idle & ((1u << g0) - 1u));
+        if (pair < npair) {
+          slot = p.ms.pair_slot[pair];
+          const int g = p.ms.pair_geom[pair];
+          const uint32_t ray = p.ms.aff_ray[slot];
+          const int scan = (int)(ray / (uint32_t)p.nray);
+          const int r = (int)(ray - (uint32_t)scan * (uint32_t)p.nray);
+          const int world = p.scan_world ? p.scan_world[scan] : (p.scan0 + scan) % p.nworld;
+          const GeomPose P = ld_pose(p.pose + (size_t)world * p.ngeom + g);
+          double o[3], l[3], vec[3];
+          scan_ray<MODE>(p, scan, r, o, l, vec);
+          ray_map(P, o, vec, lpnt, lvec);
+          mesh_ray_basis(lvec, b0, b1);
+          rayf_setup(rf, lpnt, lvec);
+          const MeshInfo mi = p.mesh[p.gstat[g].dataid];
+          nodes = p.mnodes + mi.node_base;
+          tris = p.mtris + mi.tri_base;
+          x = -1;
+          have = true;
+        }
+      }
+      // the bound other pairs of the ray have published so far: read by one lane, so that every lane
+      // of the group starts from the same tmax
+      unsigned long long best = kInfBits;
+      if (fresh && have && gl == 0)
+        best = *reinterpret_cast<volatile unsigned long long*>(p.ms.aff_bits + slot);
+      best = __shfl_sync(0xffffffffu, best, g0);
+      if (fresh && have) {
+        tmax = best == kInfBits ? tcap : fminf(tcap, f32_up(__longlong_as_double((long long)best)));
+        if (gl == 0) stk[0] = make_uint2(0u, 0u);  // the root, entry distance 0
+        sp = 1;
+      }
+      __syncwarp();
+    }
+    if (!__any_sync(0xffffffffu, have)) break;
+
+    // (2) pop: quad q takes entry q from the top; only one entry while the stack is near its cap
+    int ntake = 0;
+    if (have) {
+      ntake = ::min(nq, sp);
+      if (sp + 3 * nq > cap_soft) ntake = 1;
+    }
+    const bool mine = quad < ntake;
+    uint2 e = make_uint2(0u, 0u);
+    if (mine) e = stk[sp - 1 - quad];
+    const int spn = sp - ntake;
+    const bool live = mine && __uint_as_float(e.y) <= tmax;
+    const int32_t link = (int32_t)e.x;
+    __syncwarp();  // every pop has read its entry before the pushes below overwrite the top
+
+    // (3) a node: this lane's child box; a leaf: this lane's triangle
+    bool hitc = false;
+    float tc = INFINITY;
+    int32_t clink = kEmptyChild;
+    if (live && link >= 0) {
+      const MeshNode4* n = nodes + link;
+      clink = __ldg(n->child + child);
+      const float lo[3] = {__ldg(n->lox + child), __ldg(n->loy + child), __ldg(n->loz + child)};
+      const float hi[3] = {__ldg(n->hix + child), __ldg(n->hiy + child), __ldg(n->hiz + child)};
+      hitc = clink != kEmptyChild && slab_test(rf, lo, hi, tmax, tc);
+      if (!hitc) tc = INFINITY;  // (slab_test leaves its entry distance behind on a miss too)
+    }
+    const bool at_leaf = live && link < 0;
+    if (__any_sync(0xffffffffu, at_leaf)) {
+      double sol = INFINITY;
+      if (at_leaf) {
+        const int32_t payload = ~link;
+        const int first = payload >> 2, cnt = (payload & 3) + 1;
+        if (child < cnt) {
+          const MeshTri tr = ld_tri(tris + first + child);
+          const double t = ray_triangle(tr.v0, tr.v1, tr.v2, lpnt, lvec, b0, b1);
+          if (t >= 0) sol = t;
+        }
+      }
+      // nearest hit of the round over the group (exact: min of doubles)
+#pragma unroll
+      for (int o = G >> 1; o > 0; o >>= 1) sol = fmin(sol, __shfl_xor_sync(0xffffffffu, sol, o));
+      if (sol < INFINITY && (x < 0 || sol < x)) {
+        x = sol;
+        tmax = fminf(tmax, f32_up(sol));
+      }
+    }
+
+    // (4) push the children that were hit: higher quads first, and within a quad the farthest first,
+    //     so that the nearest child of the top entry ends on top
+    const unsigned hm = __ballot_sync(0xffffffffu, hitc);
+    if (hm) {        // (warp-uniform: the shuffles below name every lane)
+      int nearer = 0;  // hit children of this quad that are nearer than this one
+#pragma unroll
+      for (int k = 1; k < 4; k++) {
+        const float tj = __shfl_xor_sync(0xffffffffu, tc, k);  // a missed child carries +inf
+        const int j = child ^ k;
+        nearer += (tj < tc || (tj == tc && j < child && tj < INFINITY)) ? 1 : 0;
+      }
+      if (hitc) {
+        const unsigned above = q0 + 4 >= 32 ? 0u : (hm & gmask & ~((1u << (q0 + 4)) - 1u));
+        const int qh = __popc(hm & (0xfu << q0));
+        const int idx = spn + __popc(above) + (qh - 1 - nearer);
+        if (idx < cap) stk[idx] = make_uint2((uint32_t)clink, __float_as_uint(tc));
+        else p.ms.counters[2] = 1;  // cannot happen (reserve >= 3 * depth + 1); the clean-up launch recomputes
+      }
+    }
+    sp = ::min(spn + __popc(hm & gmask), cap);
+    __syncwarp();
+
+    // (5) pair finished: publish
+    if (have && sp == 0) {
+      if (gl == 0) {
+        p.ms.pair_x[pair] = x;
+        if (x >= 0) atomicMin(p.ms.aff_bits + slot, (unsigned long long)__double_as_longlong(x));
+      }
+      have = false;
+    }
+  }
+}
+
+#ifndef B2_COOP_MINBLOCKS
+#define B2_COOP_MINBLOCKS 8
+#endif
+template <int MODE>
+__global__ void __launch_bounds__(kMeshThreads, B2_COOP_MINBLOCKS)
+    mesh_pairs_coop_kernel(const __grid_constant__ CastParams p, int g_req) {
+  const int npair = ::min(p.ms.counters[0], p.ms.pair_cap);
+  __shared__ uint2 s_stk[kMeshThreads / 32][kCoopStackPerWarp];
+  uint2* warp_stk = s_stk[threadIdx.x >> 5];
+  // group width: a whole warp per pair while that leaves every resident warp at most ~3 pairs
+  // (one 64x2048 scan: 11 k pairs, 4736 warps; 133.7 us per scan against 134.5 at 16 lanes and 159.3
+  // with one lane per pair), half a warp beyond (two scans: 200 / 207 / 219 us at 16 / 32 / 1 lanes)
+  const int nwarp = (int)gridDim.x * (kMeshThreads / 32);
+  const int G = (g_req == 8 || g_req == 16 || g_req == 32) ? g_req : (npair <= 3 * nwarp ? 32 : 16);
+  if (G == 32) mesh_pairs_coop<MODE, 32>(p, npair, warp_stk);
+  else if (G == 16) mesh_pairs_coop<MODE, 16>(p, npair, warp_stk);
+  else mesh_pairs_coop<MODE, 8>(p, npair, warp_stk);
+}
+
 // K2c: lowest mesh geom id among the pairs that reached the ray's minimum (A.5 tie rule)
 __global__ void __launch_bounds__(kMeshThreads) mesh_ids_kernel(const __grid_constant__ CastParams p) {
   const int npair = ::min(p.ms.counters[0], p.ms.pair_cap);
@@ -866,6 +1050,10 @@ static cudaError_t launch_two_kernel(const CastParams& p, const TileGeom& tg, bo
 }
 
 // B2_VEC_OUT=0 turns the float4 / int4 result stores of K2b off (A/B runs)
+static int env_int_local(const char* name, int dflt) {
+  const char* v = std::getenv(name);
+  return v ? std::atoi(v) : dflt;
+}
 static bool env_flag_vec_out() {
   const char* v = std::getenv("B2_VEC_OUT");
   return !(v && v[0] == '0');
@@ -941,7 +1129,15 @@ static cudaError_t launch_cast_mode(const CastParams& p, bool stage, int tiles_p
   if (err != cudaSuccess) return err;
   const unsigned mgrid = (unsigned)(sm_count * 16);
   // persistent: exactly the CTAs that are resident at once
-  mesh_pairs_kernel<MODE><<<(unsigned)(sm_count * B2_MESH_MINBLOCKS), kMeshThreads, 0, stream>>>(p);
+  // a launch of one or two scans (the plugin's duty cycle: one scan per publish) is as long as its
+  // heaviest pair: G lanes per pair there.  From four 64x2048 scans on, the one-lane kernel wins
+  // (tools/latency_probe.py --coop: 1 / 2 / 4 / 8 scans 134 / 200 / 305 / 441 us against 159 / 219 / 269 / 367)
+  const int coop_rays = env_int_local("B2_MESH_COOP_RAYS", 1 << 18);
+  const int coop_g = env_int_local("B2_MESH_COOP_G", 0);
+  if ((long long)p.nscan * p.nray <= coop_rays)
+    mesh_pairs_coop_kernel<MODE><<<(unsigned)(sm_count * B2_COOP_MINBLOCKS), kMeshThreads, 0, stream>>>(p, coop_g);
+  else
+    mesh_pairs_kernel<MODE><<<(unsigned)(sm_count * B2_MESH_MINBLOCKS), kMeshThreads, 0, stream>>>(p);
   mesh_ids_kernel<<<mgrid, kMeshThreads, 0, stream>>>(p);
   mesh_final_kernel<MODE><<<mgrid, kMeshThreads, 0, stream>>>(p);
   err = cudaGetLastError();

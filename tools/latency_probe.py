@@ -21,30 +21,37 @@ def main():
     sc = engine.Scene(cs.model, nworld=1, device=0)
     sc.update_poses(cs.poses)
     lid = engine.Lidar(sc, cs.lidar)
-    pos, mat = cs.sensor_poses(2)
-    bufs = {"ranges": np.empty((1, lid.nray), np.float32)}
+    nscan = 1
+    for a in sys.argv[1:]:
+        if a.startswith("--nscan="):
+            nscan = int(a.split("=")[1])       # several scans per call: where the small-launch paths hand over
+    pos, mat = cs.sensor_poses(nscan + 1)
+    bufs = {"ranges": np.empty((nscan, lid.nray), np.float32)}
     profiling = "--profile" in sys.argv
     for _ in range(5):
-        lid.cast(pos[1:2], mat[1:2], want=("ranges",), out=bufs)
+        lid.cast(pos[1:], mat[1:], want=("ranges",), out=bufs)
     if profiling:
         os.environ["B2_GRAPH"] = "0"  # plain launches: ncu lists the kernels of the sequence
-        lid.cast(pos[1:2], mat[1:2], want=("ranges",), out=bufs)
+        lid.cast(pos[1:], mat[1:], want=("ranges",), out=bufs)
         torch.cuda.profiler.start()
-        lid.cast(pos[1:2], mat[1:2], want=("ranges",), out=bufs)
+        lid.cast(pos[1:], mat[1:], want=("ranges",), out=bufs)
         torch.cuda.profiler.stop()
         return
-    for env in ({}, {"B2_GRAPH": "0"}, {"B2_SPLIT": "0"}, {"B2_SPLIT": "0", "B2_GRAPH": "0"},
-                {"B2_SMALL_SPLIT": "0"}, {"B2_TWO_MIN_RAYS": "1"}):
-        for k in ("B2_GRAPH", "B2_SPLIT", "B2_SMALL_SPLIT", "B2_TWO_MIN_RAYS"):
+    envs = ({}, {"B2_GRAPH": "0"}, {"B2_MESH_COOP_RAYS": "0"}, {"B2_MESH_COOP_G": "8"}, {"B2_MESH_COOP_G": "16"},
+            {"B2_MESH_COOP_G": "32"}, {"B2_SPLIT": "0"}, {"B2_SMALL_SPLIT": "0"}, {"B2_TWO_MIN_RAYS": "1"})
+    if "--coop" in sys.argv:
+        envs = ({"B2_MESH_COOP_RAYS": "0"}, {"B2_MESH_COOP_G": "8"}, {"B2_MESH_COOP_G": "16"}, {"B2_MESH_COOP_G": "32"}, {})
+    for env in envs:
+        for k in ("B2_GRAPH", "B2_SPLIT", "B2_SMALL_SPLIT", "B2_TWO_MIN_RAYS", "B2_MESH_COOP_RAYS", "B2_MESH_COOP_G"):
             os.environ.pop(k, None)
         os.environ.update(env)
         lid2 = engine.Lidar(sc, cs.lidar)  # a fresh lidar: its graph is captured under this setting
         for _ in range(5):
-            lid2.cast(pos[1:2], mat[1:2], want=("ranges",), out=bufs)
+            lid2.cast(pos[1:], mat[1:], want=("ranges",), out=bufs)
         wall, dev = [], []
         for _ in range(200):
             t0 = time.perf_counter()
-            lid2.cast(pos[1:2], mat[1:2], want=("ranges",), out=bufs)
+            lid2.cast(pos[1:], mat[1:], want=("ranges",), out=bufs)
             wall.append((time.perf_counter() - t0) * 1e6)
             dev.append(lid2.last_device_us())
         print(f"{str(env):50s} host p50 {np.median(wall):7.1f} us  device p50 {np.median(dev):7.1f} us")
