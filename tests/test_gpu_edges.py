@@ -128,6 +128,39 @@ def test_mesh_heavy_scene_in_place_and_split_paths(oracle):
     assert hit.max() < len(keep)          # a coincident copy (higher id) never wins a tie
 
 
+@pytest.mark.parametrize("env", [{"B2_MESH_COOP_G": "8"}, {"B2_MESH_COOP_G": "16"}, {"B2_MESH_COOP_G": "32"},
+                                 {"B2_MESH_COOP_RAYS": "0"}])
+def test_mesh_pairs_of_a_small_launch_every_group_width(oracle, env):
+    """a launch of one or two scans traces its (ray, mesh) pairs with a GROUP of lanes per pair (shared
+    stack, several nodes / triangles per round): every group width, and the one-lane kernel, give the
+    oracle's bits -- on the cluttered scene (one 64x2048 scan) and on the mesh-only scene with
+    coincident instances"""
+    import os
+    old = {k: os.environ.get(k) for k in ("B2_MESH_COOP_G", "B2_MESH_COOP_RAYS")}
+    os.environ.update(env)
+    try:
+        cs = scenes.clutter500()
+        sc = engine.Scene(cs.model, nworld=1)
+        sc.update_poses(cs.poses)
+        lid = engine.Lidar(sc, cs.lidar)
+        pos, mat = cs.sensor_poses(3, seed=11)
+        out = lid.cast(pos[2:3], mat[2:3], want=("ranges", "geomid", "dist"))
+        o = oracle.OracleScene(cs.model, cs.poses)
+        r, g, raw = o.lidar_scan(cs.lidar, pos[2], mat[2], nthread=8)
+        assert np.array_equal(out["geomid"][0], g) and np.array_equal(out["dist"][0], raw)
+        assert np.array_equal(out["ranges"][0], r)
+        assert (cs.model.geom_type[g[g >= 0]] == 7).mean() > 0.02     # meshes do win rays here
+        lid.close()
+        sc.close()
+        test_mesh_heavy_scene_in_place_and_split_paths(oracle)
+    finally:
+        for k, v in old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+
+
 def test_rgb_flip_kernel():
     import torch
     dev = torch.device("cuda", 0)
