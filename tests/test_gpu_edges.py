@@ -161,6 +161,46 @@ def test_mesh_pairs_of_a_small_launch_every_group_width(oracle, env):
                 os.environ[k] = v
 
 
+def test_camera_frame_same_bits_on_every_mesh_path():
+    """a 320x240 ray-cast depth frame (76 800 primary rays: the group mesh kernel in camera mode) has the
+    bits of the one-lane mesh kernel and of the in-place mesh tracing"""
+    import os
+
+    import torch
+    cs = scenes.clutter500(n_el=16, n_az=128)
+    sc = engine.Scene(cs.model, nworld=1)
+    sc.update_poses(cs.poses)
+    cam = engine.DepthCamera(scenes.CameraSpec(320, 240, 58.0, 0.01, 50.0, 1.0, 12, geomgroup=(1,) * 6), scene=sc)
+    dev = torch.device("cuda", 0)
+    R = np.array([[0, 0, -1.0], [-1.0, 0, 0], [0, 1.0, 0]]).reshape(1, 9)
+    d_pos = torch.from_numpy(np.array([[3.0, 0.0, 1.5]])).to(dev)
+    d_mat = torch.from_numpy(R).to(dev)
+    frames = {}
+    keys = ("B2_MESH_COOP_RAYS", "B2_MESH_COOP_G", "B2_SPLIT")
+    old = {k: os.environ.get(k) for k in keys}
+    try:
+        for name, env in (("group", {}), ("group16", {"B2_MESH_COOP_G": "16"}), ("one_lane", {"B2_MESH_COOP_RAYS": "0"}),
+                          ("in_place", {"B2_SPLIT": "0"})):
+            for k in keys:
+                os.environ.pop(k, None)
+            os.environ.update(env)
+            gl = torch.full((1, 240, 320), -1.0, dtype=torch.float32, device=dev)
+            cam.render_depth_device(1, d_pos, d_mat, gl)
+            sc.sync()
+            frames[name] = gl.cpu().numpy()
+    finally:
+        for k, v in old.items():
+            os.environ.pop(k, None)
+            if v is not None:
+                os.environ[k] = v
+    f = frames["group"]
+    assert 0.05 < (f < 1.0).mean() and f.min() >= 0.0 and f.max() <= 1.0
+    for name in ("group16", "one_lane", "in_place"):
+        assert np.array_equal(frames[name], f), name
+    cam.close()
+    sc.close()
+
+
 def test_rgb_flip_kernel():
     import torch
     dev = torch.device("cuda", 0)
