@@ -247,6 +247,17 @@ __device__ __forceinline__ void store_patch(const CastParams& p, const TileGeom&
   }
 }
 
+#ifdef B2_MESH_STATS
+__device__ unsigned long long g_tile_stats[32];
+extern "C" int b2_debug_tile_stats(unsigned long long* out, int reset) {
+  if (out) cudaMemcpyFromSymbol(out, g_tile_stats, sizeof(g_tile_stats));
+  if (reset) {
+    unsigned long long z[32] = {0};
+    cudaMemcpyToSymbol(g_tile_stats, z, sizeof(z));
+  }
+  return 0;
+}
+#endif
 // ONLY_IF_OVERFLOW: the clean-up launch -- exits at once unless the split pass overflowed
 template <int MODE, bool STAGE, bool SPLIT, bool ONLY_IF_OVERFLOW>
 __global__ void __launch_bounds__(kCastThreads, B2_CAST_MINBLOCKS)
@@ -323,7 +334,20 @@ __global__ void __launch_bounds__(kCastThreads, B2_CAST_MINBLOCKS)
     for (int k = 0; k < 3; k++) o[k] = __ldg(p.spos + (size_t)scan * 3 + k);
     const GroupGen<MODE> gen{p, tg, scan, tile0, lane};
     const GroupEpi<MODE, SPLIT> epi{p, tg, scan, tile0, lane};
+#ifdef B2_MESH_STATS
+    const long long st_t0 = clock64();
+#endif
     trace_group<STAGE>(p, wslots, wnodes, elim, pose, nt, o, tcap, warp, gen, epi);
+#ifdef B2_MESH_STATS
+    if (lane == 0 && !ONLY_IF_OVERFLOW) {  // per tile group of the fused kernel (tools/mesh_stats.py --tiles)
+      const unsigned long long cyc = (unsigned long long)(clock64() - st_t0);
+      atomicAdd(g_tile_stats + 0, 1ull);
+      atomicAdd(g_tile_stats + 1, cyc);
+      atomicMax(g_tile_stats + 2, cyc);
+      atomicMax(g_tile_stats + 3, (unsigned long long)(clock64() & 0xffffffffffffll));
+      atomicAdd(g_tile_stats + 16 + ::min(15, ::max(0, 64 - __clzll(cyc) - 8)), 1ull);  // log2 histogram of cycles / 256
+    }
+#endif
   }
 }
 

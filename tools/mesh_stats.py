@@ -36,6 +36,15 @@ def main():
     print("log2 histogram of nodes :", [int(v) for v in s[16:32]])
     print("log2 histogram of tris  :", [int(v) for v in s[32:48]])
     print("log2 histogram of cyc/256:", [int(v) for v in s[48:64]])
+    if hasattr(lib, "b2_debug_tile_stats"):
+        t = (C.c_ulonglong * 32)()
+        lib.b2_debug_tile_stats(None, 1)
+        lid.cast(pos[1:], mat[1:], want=("ranges",), out=bufs)
+        lib.b2_debug_tile_stats(t, 0)
+        t = np.array(t[:], dtype=np.float64)
+        n = max(t[0], 1)
+        print(f"fused kernel: tile groups {int(t[0])}  cycles / group mean {t[1]/n:8.0f}  max {int(t[2])}")
+        print("log2 histogram of cyc/256:", [int(v) for v in t[16:32]])
 
 
 if __name__ == "__main__":
