@@ -10,7 +10,7 @@ import subprocess
 import sys
 
 LIB = sys.argv[1] if len(sys.argv) > 1 else "mujoco_ros2_simulation_b200/libb2sense.so"
-KERNELS = ["collect_kernelILi0ELb1E", "drain_kernelILi0ELb1E", "mesh_pairs_kernelILi0E", "mesh_ids_kernel",
+KERNELS = ["collect_kernelILi0ELb1E", "drain_kernelILi0ELb1E", "mesh_pairs_kernelILi0E", "mesh_pairs_coop_kernelILi0E", "mesh_ids_kernel",
            "mesh_final_kernelILi0E", "cast_kernelILi0ELb1ELb1ELb0E", "refit_kernel", "depth_to_cloud_kernel",
            "rgb_flip_kernel"]
 
