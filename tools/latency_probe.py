@@ -17,7 +17,8 @@ def main():
     import torch
 
     from mujoco_ros2_simulation_b200 import engine, scenes
-    cs = scenes.clutter500()
+    robot = "--robot" in sys.argv     # the reference's fixture: 6 boxes, 360-ray planar lidar (cfg1)
+    cs = scenes.robot_scene(n_rays=360) if robot else scenes.clutter500()
     sc = engine.Scene(cs.model, nworld=1, device=0)
     sc.update_poses(cs.poses)
     lid = engine.Lidar(sc, cs.lidar)
@@ -25,7 +26,11 @@ def main():
     for a in sys.argv[1:]:
         if a.startswith("--nscan="):
             nscan = int(a.split("=")[1])       # several scans per call: where the small-launch paths hand over
-    pos, mat = cs.sensor_poses(nscan + 1)
+    if robot:
+        pos = np.repeat(cs.lidar_pos[None], 2, 0)
+        mat = np.repeat(cs.lidar_mat.reshape(1, 9), 2, 0)
+    else:
+        pos, mat = cs.sensor_poses(nscan + 1)
     bufs = {"ranges": np.empty((nscan, lid.nray), np.float32)}
     profiling = "--profile" in sys.argv
     for _ in range(5):
