@@ -200,6 +200,7 @@ struct b2_lidar {
   DevBuf<uint8_t> d_elim;
   // scratch of the host-pointer entry point
   DevBuf<double> d_spos, d_smat, d_dist;
+  DevBuf<double> d_in;  // small path: pos | mat | world of the call in one block (one H2D copy)
   DevBuf<int32_t> d_world, d_geomid;
   DevBuf<uint16_t> d_geomid16;
   DevBuf<float> d_ranges, d_xyz;
@@ -1026,6 +1027,7 @@ int b2_lidar_destroy(b2_lidar* l) {
   l->d_local_dir.release();
   l->d_elim.release();
   l->d_spos.release();
+  l->d_in.release();
   l->d_smat.release();
   l->d_dist.release();
   l->d_world.release();
@@ -1122,15 +1124,12 @@ constexpr long long kSmallCastRays = 1 << 20;  // below this a host cast is one 
 // the results into pinned staging -- all on the scene's stream, all addresses fixed per lidar
 int enqueue_small(b2_lidar* l, const HostCast& hc, bool has_world, cudaStream_t stream) {
   const size_t ns = (size_t)hc.nscan, n = hc.n;
-  B2_CUDA(cudaMemcpyAsync(l->d_spos.ptr, l->h_in.ptr, ns * 3 * sizeof(double),
+  // sensor frames (and the world table): one copy of the staging block, laid out pos | mat | world
+  double* d_in = l->d_in.ptr;
+  B2_CUDA(cudaMemcpyAsync(d_in, l->h_in.ptr, ns * 12 * sizeof(double) + (has_world ? ns * sizeof(int32_t) : 0),
                           cudaMemcpyHostToDevice, stream));
-  B2_CUDA(cudaMemcpyAsync(l->d_smat.ptr, l->h_in.ptr + ns * 3, ns * 9 * sizeof(double),
-                          cudaMemcpyHostToDevice, stream));
-  if (has_world)
-    B2_CUDA(cudaMemcpyAsync(l->d_world.ptr, l->h_in.ptr + ns * 12, ns * sizeof(int32_t),
-                            cudaMemcpyHostToDevice, stream));
-  int rc = lidar_launch(l, hc.nscan, 0, has_world ? l->d_world.ptr : nullptr, l->d_spos.ptr,
-                        l->d_smat.ptr, hc.ranges ? l->d_ranges.ptr : nullptr,
+  int rc = lidar_launch(l, hc.nscan, 0, has_world ? reinterpret_cast<const int32_t*>(d_in + ns * 12) : nullptr,
+                        d_in, d_in + ns * 3, hc.ranges ? l->d_ranges.ptr : nullptr,
                         hc.geomid ? l->d_geomid.ptr : nullptr,
                         hc.geomid16 ? l->d_geomid16.ptr : nullptr, hc.dist ? l->d_dist.ptr : nullptr,
                         hc.xyz ? l->d_xyz.ptr : nullptr, stream);
@@ -1217,6 +1216,7 @@ int lidar_cast_begin(b2_lidar* l, int32_t nscan, const int32_t* scan_world, cons
     // ---- small path: one piece; the whole sequence is captured into a CUDA graph the second time
     //      the same shape is asked for (a single scan is ~6 launches + copies: launch-gap bound)
     B2_CUDA(l->h_in.reserve(ns * 13 + 16));
+    B2_CUDA(l->d_in.reserve(ns * 13 + 16));
     std::memcpy(l->h_in.ptr, sensor_pos, ns * 3 * sizeof(double));
     std::memcpy(l->h_in.ptr + ns * 3, sensor_mat, ns * 9 * sizeof(double));
     if (scan_world) std::memcpy(l->h_in.ptr + ns * 12, scan_world, ns * sizeof(int32_t));
