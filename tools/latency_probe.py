@@ -44,10 +44,13 @@ def main():
         return
     envs = ({}, {"B2_GRAPH": "0"}, {"B2_MESH_COOP_RAYS": "0"}, {"B2_MESH_COOP_G": "8"}, {"B2_MESH_COOP_G": "16"},
             {"B2_MESH_COOP_G": "32"}, {"B2_SPLIT": "0"}, {"B2_SMALL_SPLIT": "0"}, {"B2_TWO_MIN_RAYS": "1"})
+    if "--group" in sys.argv:
+        envs = ({}, {"B2_SMALL_SPLIT": "0", "B2_GROUP_TILES_RT": "2"}, {"B2_SMALL_SPLIT": "0", "B2_GROUP_TILES_RT": "4"})
     if "--coop" in sys.argv:
         envs = ({"B2_MESH_COOP_RAYS": "0"}, {"B2_MESH_COOP_G": "8"}, {"B2_MESH_COOP_G": "16"}, {"B2_MESH_COOP_G": "32"}, {})
     for env in envs:
-        for k in ("B2_GRAPH", "B2_SPLIT", "B2_SMALL_SPLIT", "B2_TWO_MIN_RAYS", "B2_MESH_COOP_RAYS", "B2_MESH_COOP_G"):
+        for k in ("B2_GRAPH", "B2_SPLIT", "B2_SMALL_SPLIT", "B2_TWO_MIN_RAYS", "B2_MESH_COOP_RAYS", "B2_MESH_COOP_G",
+                  "B2_GROUP_TILES_RT"):
             os.environ.pop(k, None)
         os.environ.update(env)
         lid2 = engine.Lidar(sc, cs.lidar)  # a fresh lidar: its graph is captured under this setting
